@@ -1,0 +1,50 @@
+"""
+Builds libamtfeat.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo
+snapshot to the GPU box).  `python -m amt_tools_b200.build` or __graft_entry__.build().
+"""
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libamtfeat.so')
+SOURCES = ['api.cpp', 'host_plan.cpp', 'kernels.cu']
+HEADERS = ['plan.h', 'fft_device.cuh', os.path.join('..', '..', 'include', 'amtfeat.h')]
+
+
+def _nvcc():
+    for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), '-O3', '-std=c++17', '-lineinfo', '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden',
+           '-gencode', 'arch=compute_100a,code=sm_100a', '-x', 'cu',
+           '-Xcompiler', '-DAMTFEAT_BUILD', '-o', LIB]
+    if verbose:
+        cmd += ['-Xptxas', '-v']
+    cmd += [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed building libamtfeat.so')
+    if verbose:
+        sys.stderr.write(res.stderr)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,168 @@
+// extern "C" surface of libamtfeat.so (declared in include/amtfeat.h).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "plan.h"
+
+struct amtfeat_plan {
+    amtfeat::Plan p;
+};
+
+namespace amtfeat {
+const char *last_error_cstr();
+}
+
+using amtfeat::Plan;
+
+extern "C" {
+
+int amtfeat_version(void) { return AMTFEAT_VERSION; }
+const char *amtfeat_last_error(void) { return amtfeat::last_error_cstr(); }
+
+int amtfeat_plan_create(const amtfeat_config *cfg, int device, amtfeat_plan **out) {
+    if (!cfg || !out) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    *out = nullptr;
+    amtfeat_plan *h = new (std::nothrow) amtfeat_plan();
+    if (!h) { amtfeat::set_error("out of memory"); return AMTFEAT_ERR_INVALID; }
+    h->p.cfg = *cfg;
+    h->p.cfg.decim_taps = nullptr;  // copied into the plan by build_plan_tables via the caller's pointer below
+    h->p.device = device;
+    int rc;
+    try {
+        amtfeat_config tmp = *cfg;
+        h->p.cfg = tmp;
+        rc = amtfeat::build_plan_tables(h->p);
+        h->p.cfg.decim_taps = nullptr;  // never keep the caller's pointer
+        h->p.cfg.n_decim_taps = 0;
+        if (rc == AMTFEAT_OK && device >= 0) rc = amtfeat::upload_plan(h->p);
+    } catch (const std::exception &e) {
+        amtfeat::set_error(std::string("exception: ") + e.what());
+        rc = AMTFEAT_ERR_INVALID;
+    }
+    if (rc != AMTFEAT_OK) {
+        amtfeat::free_plan_device(h->p);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return AMTFEAT_OK;
+}
+
+void amtfeat_plan_destroy(amtfeat_plan *plan) {
+    if (!plan) return;
+    amtfeat::free_plan_device(plan->p);
+    delete plan;
+}
+
+int64_t amtfeat_expected_frames(const amtfeat_plan *plan, int64_t n) { return amtfeat::expected_frames(plan->p, n); }
+int64_t amtfeat_output_frames(const amtfeat_plan *plan, int64_t n) { return amtfeat::output_frames(plan->p, n); }
+
+int amtfeat_sample_range(const amtfeat_plan *plan, int64_t frames, int64_t *lo, int64_t *hi) {
+    return amtfeat::sample_range(plan->p, frames, lo, hi);
+}
+
+int64_t amtfeat_num_samples_required(const amtfeat_plan *plan) {
+    int64_t lo = 0, hi = 0;
+    amtfeat::sample_range(plan->p, 1, &lo, &hi);
+    return hi;
+}
+
+int amtfeat_times(const amtfeat_plan *plan, int64_t n, int at_start, double *out, int64_t capacity) {
+    const Plan &p = plan->p;
+    const amtfeat_config &c = p.cfg;
+    const int64_t T = amtfeat::expected_frames(p, n);
+    if (T > capacity) { amtfeat::set_error("times buffer too small"); return AMTFEAT_ERR_INVALID; }
+    const double sr = c.sample_rate;
+    // librosa.frames_to_time: (frames * hop).astype(int) / float(sr)   (common.py:250-256)
+    for (int64_t t = 0; t < T; ++t) out[t] = (double)(t * (int64_t)c.hop_length) / sr;
+    double shift = 0.0;
+    bool sub = false, add = false;
+    if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
+        if (at_start) {  // vqt.py:217-225 (intended behaviour): floor(L_fmin / 2) / sr with the reference's own alpha
+            const double alpha = std::pow(2.0, 1.0 / c.bins_per_octave) - 1;
+            const double len = (1.0 / alpha) * sr / (p.harm[0].fmin + c.gamma / alpha);
+            shift = std::floor(len / 2.0) / sr;
+            sub = true;
+        }
+    } else {
+        shift = (double)(c.win_length / 2) / sr;  // waveform.py:175-180
+        sub = c.center && at_start;
+        add = !c.center && !at_start;
+    }
+    if (sub) for (int64_t t = 0; t < T; ++t) out[t] -= shift;
+    if (add) for (int64_t t = 0; t < T; ++t) out[t] += shift;
+    return AMTFEAT_OK;
+}
+
+int amtfeat_early_ds_count(const amtfeat_plan *plan, int h) {
+    if (h < 0 || h >= (int)plan->p.harm.size()) return -1;
+    return plan->p.harm[h].eds_ref;
+}
+
+int amtfeat_num_channels(const amtfeat_plan *plan) { return plan->p.C; }
+int amtfeat_feature_size(const amtfeat_plan *plan) { return plan->p.F; }
+
+int amtfeat_out_shape(const amtfeat_plan *plan, int64_t n, int64_t shape[3], int *ndim) {
+    const Plan &p = plan->p;
+    const amtfeat_config &c = p.cfg;
+    const int64_t T = amtfeat::output_frames(p, n);
+    if (T < 0) { amtfeat::set_error("input too short for an uncentered frame"); return AMTFEAT_ERR_INVALID; }
+    switch (c.kind) {
+        case AMTFEAT_POWER: *ndim = 1; shape[0] = T; shape[1] = shape[2] = 1; break;
+        case AMTFEAT_WAVEFORM: *ndim = 2; shape[0] = c.win_length; shape[1] = T; shape[2] = 1; break;
+        case AMTFEAT_STFT:  // stft.py:59 returns (1, n_fft, 0) for empty audio
+            *ndim = 3; shape[0] = 1; shape[1] = n == 0 ? c.n_fft : p.F; shape[2] = T; break;
+        default: *ndim = 3; shape[0] = p.C; shape[1] = p.F; shape[2] = T; break;
+    }
+    return AMTFEAT_OK;
+}
+
+int amtfeat_plan_describe(const amtfeat_plan *plan, char *buf, size_t capacity) {
+    const std::string s = amtfeat::describe(plan->p);
+    if (s.size() + 1 > capacity) { amtfeat::set_error("describe buffer too small"); return AMTFEAT_ERR_INVALID; }
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return AMTFEAT_OK;
+}
+
+size_t amtfeat_workspace_bytes(const amtfeat_plan *plan, int batch, const int64_t *n) {
+    return amtfeat::workspace_bytes(plan->p, batch, n);
+}
+
+int amtfeat_launch_count(const amtfeat_plan *plan, int batch, const int64_t *n) {
+    return amtfeat::launch_count(plan->p, batch, n);
+}
+
+int amtfeat_process(const amtfeat_plan *plan, const float *d_audio, const int64_t *in_offsets, const int64_t *num_samples,
+                    const int64_t *out_offsets, int batch, float *d_out, void *d_workspace, size_t workspace_bytes,
+                    void *stream) {
+    if (!plan || !in_offsets || !num_samples || !out_offsets) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    try {
+        return amtfeat::process(plan->p, d_audio, in_offsets, num_samples, out_offsets, batch, d_out, d_workspace,
+                                workspace_bytes, stream);
+    } catch (const std::exception &e) {
+        amtfeat::set_error(std::string("exception: ") + e.what());
+        return AMTFEAT_ERR_INVALID;
+    }
+}
+
+int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const int64_t *in_offsets,
+                         const int64_t *num_samples, const int64_t *out_offsets, int batch, float *h_out,
+                         int64_t audio_elems, int64_t out_elems, float *d_audio, float *d_out, void *d_workspace,
+                         size_t workspace_bytes, void *stream) {
+    if (!plan) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    if (plan->p.device < 0) { amtfeat::set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemcpyAsync(d_audio, h_audio, (size_t)audio_elems * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { amtfeat::set_error(std::string("H2D: ") + cudaGetErrorString(e)); return AMTFEAT_ERR_CUDA; }
+    int rc = amtfeat_process(plan, d_audio, in_offsets, num_samples, out_offsets, batch, d_out, d_workspace, workspace_bytes, stream);
+    if (rc != AMTFEAT_OK) return rc;
+    e = cudaMemcpyAsync(h_out, d_out, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { amtfeat::set_error(std::string("D2H: ") + cudaGetErrorString(e)); return AMTFEAT_ERR_CUDA; }
+    return AMTFEAT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+// Host side of a plan: validation, constant-table design (window, mel filterbank, decimator taps,
+// sparsified frequency-domain wavelet bases, FFT twiddles) and the integer / float64 frame arithmetic
+// of the reference's FeatureModule API.  No CUDA here.
+//
+// The table design restates, in double precision, what the reference obtains from librosa at run
+// time (paths under /root/reference/amt_tools/features/):
+//   window        stft.py:66   librosa.stft(window='hann')           periodic Hann, centre-padded to n_fft
+//   mel           mel.py:64    librosa.filters.mel(norm='slaney')    Slaney / HTK scale
+//   wavelet basis vqt.py:183   librosa.vqt -> __vqt_filter_fft       wavelet(), FFT, sparsify_rows(0.01)
+//   decimator     vqt.py:183   librosa.resample(res_type='soxr_hq')  Kaiser-windowed sinc, soxr HQ recipe
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "plan.h"
+
+namespace amtfeat {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+const char *last_error_cstr() { return g_error.c_str(); }
+
+static const double kPi = 3.14159265358979323846264338327950288;
+static const double kHannBandwidth = 1.50018310546875;  // librosa.filters.window_bandwidth('hann')
+
+static inline int64_t floordiv(int64_t a, int64_t b) {
+    int64_t q = a / b, r = a % b;
+    return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+static inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+static int num_two_factors(int64_t x) {
+    if (x <= 0) return 0;
+    int n = 0;
+    while ((x & 1) == 0) { ++n; x >>= 1; }
+    return n;
+}
+static bool is_wave_kind(int k) {
+    return k == AMTFEAT_WAVEFORM || k == AMTFEAT_STFT || k == AMTFEAT_MEL || k == AMTFEAT_POWER;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame / sample arithmetic
+// ------------------------------------------------------------------------------------------------
+
+static int64_t vqt_expected(const Plan &p, int h, int64_t n) {
+    // vqt.py:118-132 : int(min(ceil(n / 2^k) // (hop // 2^k)) + 1), k = eds .. eds + n_oct - 1
+    const int eds = p.harm[h].eds_ref;
+    double best = INFINITY;
+    for (int k = eds; k < eds + p.n_oct; ++k) {
+        double sig = std::ceil((double)n / std::ldexp(1.0, k));
+        int64_t hopk = p.cfg.hop_length >> k;
+        double hops = hopk > 0 ? std::floor(sig / (double)hopk) : INFINITY;
+        best = std::min(best, hops + 1.0);
+    }
+    return std::isfinite(best) ? (int64_t)best : 0;
+}
+
+int64_t expected_frames(const Plan &p, int64_t n) {
+    const amtfeat_config &c = p.cfg;
+    if (is_wave_kind(c.kind)) {
+        if (c.center || n == 0) return n == 0 ? 0 : 1 + n / c.hop_length;           // common.py:62-64
+        return 1 + (floordiv(std::max<int64_t>(0, n - c.win_length) - 1, c.hop_length) + 1);  // waveform.py:64
+    }
+    int64_t best = INT64_MAX;
+    for (size_t h = 0; h < p.harm.size(); ++h) best = std::min(best, vqt_expected(p, (int)h, n));  // hvqt.py:77-81
+    return best;
+}
+
+void level_lengths(const Plan &p, int64_t n, int32_t *len) {
+    int64_t cur = n;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        len[l] = (int32_t)cur;
+        cur = (cur + 1) / 2;  // librosa.resample output length ceil(n * ratio)
+    }
+}
+
+static int64_t vqt_lib_frames(const Plan &p, int h, int64_t n) {
+    if (n == 0) return 0;
+    int32_t len[kMaxLevels];
+    level_lengths(p, n, len);
+    int64_t best = INT64_MAX;
+    for (int i = 0; i < p.n_oct; ++i) {
+        int l = p.harm[h].eds_lib + i;
+        int64_t hopl = p.cfg.hop_length >> l;
+        best = std::min<int64_t>(best, 1 + len[l] / hopl);  // centred STFT of the level signal
+    }
+    return best;
+}
+
+static int64_t padded_uncentered(const Plan &p, int64_t n) {
+    // common.py:141-166 frame_pad: pad to a multiple of win (if n <= win) else of hop
+    const int64_t required = p.cfg.win_length;  // get_sample_range(1)[-1] of the non-centred wrapper
+    int64_t divisor = n > required ? p.cfg.hop_length : required;
+    return (n + divisor - 1) / divisor * divisor;
+}
+
+int64_t output_frames(const Plan &p, int64_t n) {
+    const amtfeat_config &c = p.cfg;
+    if (n == 0) return 0;
+    switch (c.kind) {
+        case AMTFEAT_STFT:
+        case AMTFEAT_MEL: {
+            int64_t np_ = c.center ? n + 2 * (c.n_fft / 2) : padded_uncentered(p, n);
+            if (np_ < c.n_fft) return -1;  // librosa.stft raises for too-short uncentred input
+            return 1 + (np_ - c.n_fft) / c.hop_length;
+        }
+        case AMTFEAT_WAVEFORM:
+        case AMTFEAT_POWER: {
+            int64_t np_ = c.center ? n + 2 * (c.win_length / 2) : padded_uncentered(p, n);
+            if (np_ < c.win_length) return -1;
+            return 1 + (np_ - c.win_length) / c.hop_length;
+        }
+        default: {
+            int64_t best = c.kind == AMTFEAT_HVQT ? expected_frames(p, n) : INT64_MAX;  // hvqt.py:123-128 trims
+            for (size_t h = 0; h < p.harm.size(); ++h) best = std::min(best, vqt_lib_frames(p, (int)h, n));
+            return best;
+        }
+    }
+}
+
+int sample_range(const Plan &p, int64_t frames, int64_t *lo, int64_t *hi) {
+    const amtfeat_config &c = p.cfg;
+    const int64_t hop = c.hop_length;
+    if (is_wave_kind(c.kind)) {
+        if (c.center || frames == 0) {  // common.py:86-95
+            if (frames <= 0) { *lo = *hi = 0; return AMTFEAT_OK; }
+            *hi = frames * hop - 1;
+            *lo = std::max<int64_t>(1, *hi - hop + 1);
+        } else if (frames == 1) {  // waveform.py:88-90
+            *lo = 1; *hi = c.win_length;
+        } else {  // waveform.py:92-94
+            int64_t base = c.win_length + (frames - 2) * hop;
+            *lo = 1 + base; *hi = hop + base;
+        }
+        return AMTFEAT_OK;
+    }
+    // vqt.py:152-163 ; hvqt.py:103 uses the highest harmonic
+    const int64_t f = (int64_t)1 << p.harm.back().eds_ref;
+    *hi = (floordiv(frames * hop, f) - 1) * f;
+    *lo = std::max<int64_t>(1, *hi - hop + 1);
+    return AMTFEAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// table design
+// ------------------------------------------------------------------------------------------------
+
+static void fft_inplace(std::vector<std::complex<double>> &a) {  // forward DFT, radix-2, n power of two
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                double ang = -2.0 * kPi * (double)k / (double)len;
+                std::complex<double> w(std::cos(ang), std::sin(ang));
+                std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+}
+
+static void build_window(Plan &p) {
+    const int n_fft = p.cfg.n_fft, win = p.cfg.win_length;
+    p.window.assign(n_fft, 0.f);
+    const int lpad = (n_fft - win) / 2;
+    for (int i = 0; i < win; ++i) {
+        double w = win == 1 ? 1.0 : 0.5 - 0.5 * std::cos(2.0 * kPi * (double)i / (double)win);
+        p.window[lpad + i] = (float)w;
+    }
+}
+
+static double hz_to_mel(double f, bool htk) {
+    if (htk) return 2595.0 * std::log10(1.0 + f / 700.0);
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m, bool htk) {
+    if (htk) return 700.0 * (std::pow(10.0, m / 2595.0) - 1.0);
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static void build_mel(Plan &p) {
+    const amtfeat_config &c = p.cfg;
+    const int n_mels = c.n_mels, nb = c.n_fft / 2 + 1;
+    const bool htk = c.htk != 0;
+    const double fmax = c.sample_rate / 2.0;
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz_to_mel(0.0, htk), m_hi = hz_to_mel(fmax, htk);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        double m = (i == n_mels + 1) ? m_hi : m_lo + (m_hi - m_lo) * (double)i / (double)(n_mels + 1);
+        mel_f[i] = mel_to_hz(m, htk);
+    }
+    p.mel_start.assign(n_mels, 0);
+    p.mel_cnt.assign(n_mels, 0);
+    p.mel_off.assign(n_mels, 0);
+    p.mel_w.clear();
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        int first = -1, last = -1;
+        std::vector<float> row(nb);
+        for (int k = 0; k < nb; ++k) {
+            double fk = (double)k * c.sample_rate / (double)c.n_fft;  // rfftfreq
+            double lower = -(mel_f[i] - fk) / fd0, upper = (mel_f[i + 2] - fk) / fd1;
+            float w = (float)std::max(0.0, std::min(lower, upper));   // weights array is float32
+            w = (float)((double)w * enorm);                           // weights *= enorm[:, newaxis]
+            row[k] = w;
+            if (w != 0.f) { if (first < 0) first = k; last = k; }
+        }
+        p.mel_off[i] = (int32_t)p.mel_w.size();
+        if (first >= 0) {
+            p.mel_start[i] = first;
+            p.mel_cnt[i] = last - first + 1;
+            p.mel_w.insert(p.mel_w.end(), row.begin() + first, row.begin() + last + 1);
+        }
+    }
+}
+
+static double bessel_i0(double x) {
+    double sum = 1.0, term = 1.0, q = x * x / 4.0;
+    for (int k = 1; k < 500; ++k) {
+        term *= q / ((double)k * (double)k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+
+// soxr 'HQ' 2:1 decimator (libsoxr 0.1.3: soxr_quality_spec + lsx_design_lpf): 20-bit precision,
+// passband to (1 - .05 / TO_3dB(rej)) * Nyq_out, stopband from Nyq_out, Kaiser window.
+static std::vector<double> design_decimator() {
+    static const double coefs[10][4] = {
+        {-6.784957e-10, 1.02856e-05, 0.1087556, -0.8988365 + .001}, {-6.897885e-10, 1.027433e-05, 0.10876, -0.8994658 + .002},
+        {-1.000683e-09, 1.030092e-05, 0.1087677, -0.9007898 + .003}, {-3.654474e-10, 1.040631e-05, 0.1087085, -0.8977766 + .006},
+        {8.106988e-09, 6.983091e-06, 0.1091387, -0.9172048 + .015},  {9.519571e-09, 7.272678e-06, 0.1090068, -0.9140768 + .025},
+        {-5.626821e-09, 1.342186e-05, 0.1083999, -0.9065452 + .05},  {-9.965946e-08, 5.073548e-05, 0.1040967, -0.7672778 + .085},
+        {1.604808e-07, -5.856462e-05, 0.1185998, -1.34824 + .1},     {-1.511964e-07, 6.363034e-05, 0.1064627, -0.9876665 + .18}};
+    const double bits = 20.0, l2db = 20.0 * std::log10(2.0);
+    const double rej = bits * l2db;
+    const double to3db = (1.6e-6 * rej - 7.5e-4) * rej + .646;
+    const double att = (bits + 1) * l2db;
+    double Fp = (1.0 - .05 / to3db) / 2.0, Fs = 1.0 / 2.0;  // relative to the input Nyquist
+    double tr_bw = std::min(.5 * (Fs - Fp), .5 * Fs);
+    const double Fc = Fs - tr_bw;
+    const double realm = std::log(tr_bw * .5 / Fc / .0005) / std::log(2.0);
+    const int i0 = std::min(9, std::max(0, (int)realm)), i1 = std::min(9, std::max(0, 1 + (int)realm));
+    const double b0 = ((coefs[i0][0] * att + coefs[i0][1]) * att + coefs[i0][2]) * att + coefs[i0][3];
+    const double b1 = ((coefs[i1][0] * att + coefs[i1][1]) * att + coefs[i1][2]) * att + coefs[i1][3];
+    const double beta = b0 + (b1 - b0) * (realm - (int)realm);
+    const double a = ((.0007528358 - 1.577737e-05 * beta) * beta + .6248022) * beta + .06186902;
+    int num_taps = (int)std::ceil(a / tr_bw + 1);
+    num_taps = (num_taps + 4 - 2) / 4 * 4 + 1;  // 1 (mod 4)
+    const int m = num_taps - 1;
+    const double mult1 = 1.0 / (.5 * m + .5), i0b = bessel_i0(beta);
+    std::vector<double> h(num_taps);
+    double sum = 0;
+    for (int i = 0; i < num_taps; ++i) {
+        double z = i - .5 * m, x = z * kPi, y = z * mult1;
+        double s = x != 0 ? std::sin(Fc * x) / x : Fc;
+        h[i] = s * bessel_i0(beta * std::sqrt(std::max(0.0, 1 - y * y))) / i0b;
+        sum += h[i];
+    }
+    for (double &v : h) v /= sum;
+    return h;
+}
+
+static void build_fft_tables(Plan &p, int nfft) {
+    const int NC = nfft / 2;
+    if (p.fft.count(NC)) return;
+    int R1, R2;
+    switch (NC) {
+        case 1024: R1 = 32; R2 = 32; break;
+        case 512: R1 = 16; R2 = 32; break;
+        case 256: R1 = 16; R2 = 16; break;
+        case 128: R1 = 8; R2 = 16; break;
+        case 64: R1 = 8; R2 = 8; break;
+        case 32: R1 = 4; R2 = 8; break;
+        default: R1 = 4; R2 = 4; break;  // 16
+    }
+    FftTables t;
+    t.tw1.resize(NC);
+    for (int k1 = 0; k1 < R1; ++k1)
+        for (int n2 = 0; n2 < R2; ++n2) {
+            double ang = -2.0 * kPi * (double)(k1 * n2) / (double)NC;
+            t.tw1[k1 * R2 + n2] = {(float)std::cos(ang), (float)std::sin(ang)};
+        }
+    t.tw2.resize(NC + 1);
+    for (int k = 0; k <= NC; ++k) {
+        double ang = -kPi * (double)k / (double)NC;
+        t.tw2[k] = {(float)std::cos(ang), (float)std::sin(ang)};
+    }
+    p.fft[NC] = std::move(t);
+}
+
+static int build_vqt(Plan &p) {
+    const amtfeat_config &c = p.cfg;
+    const int bpo = c.bins_per_octave, n_bins = c.n_bins;
+    if (n_bins < 1 || bpo < 1) { set_error("n_bins and bins_per_octave must be positive"); return AMTFEAT_ERR_INVALID; }
+    if (c.fmin <= 0 || c.gamma < 0) { set_error("fmin must be positive and gamma non-negative"); return AMTFEAT_ERR_INVALID; }
+    p.n_oct = (int)std::ceil((double)n_bins / bpo);
+    p.n_filters = std::min(bpo, n_bins);
+    const double sr0 = c.sample_rate, nyq = sr0 / 2.0;
+    const double r = std::pow(2.0, 1.0 / bpo);
+    const double alpha_lib = (r * r - 1) / (r * r + 1);       // librosa >= 0.10 relative bandwidth
+    const double alpha_ref = std::pow(2.0, 1.0 / bpo) - 1;    // vqt.py:49 (reference's own, old convention)
+    const double Q = 1.0 / alpha_lib;
+    if (num_two_factors(c.hop_length) < p.n_oct - 1) {
+        char b[160];
+        snprintf(b, sizeof b, "hop_length must be a positive integer multiple of 2^%d for %d-octave CQT/VQT", p.n_oct - 1, p.n_oct);
+        set_error(b);
+        return AMTFEAT_ERR_INVALID;
+    }
+    std::vector<double> tapsd;
+    if (c.n_decim_taps > 0 && c.decim_taps) {
+        if (c.n_decim_taps % 2 == 0) { set_error("decimator taps must have odd length (linear phase, integer delay)"); return AMTFEAT_ERR_INVALID; }
+        tapsd.assign(c.decim_taps, c.decim_taps + c.n_decim_taps);
+    } else {
+        tapsd = design_decimator();
+    }
+    if (((tapsd.size() - 1) / 2) % 2 != 0) {  // keep the group delay even so both polyphase branches are integer-aligned
+        tapsd.insert(tapsd.begin(), 0.0);
+        tapsd.push_back(0.0);
+    }
+    p.taps.resize(tapsd.size());
+    for (size_t i = 0; i < tapsd.size(); ++i) p.taps[i] = (float)(tapsd[i] * std::sqrt(2.0));
+
+    p.harm.clear();
+    p.n_levels = 0;
+    std::map<std::pair<int, int>, std::vector<CqtRow>> groups;  // (nfft, level) -> rows
+    for (int h = 0; h < c.n_harmonics; ++h) {
+        HarmonicInfo hi;
+        hi.fmin = c.harmonics[h] * c.fmin;  // hvqt.py:47
+        std::vector<double> freqs(n_bins);
+        for (int i = 0; i < n_bins; ++i) freqs[i] = hi.fmin * std::pow(2.0, (double)i / bpo);
+        const double fmax = freqs[n_bins - 1];
+        // reference: vqt.py:81-98
+        const double cutoff_ref = fmax * (1 + 0.5 * kHannBandwidth * alpha_ref) + 0.5 * c.gamma;
+        // librosa.filters.wavelet_lengths
+        const double cutoff_lib = fmax * (1 + 0.5 * kHannBandwidth / Q) + 0.5 * c.gamma;
+        if (cutoff_lib > nyq) {
+            char b[200];
+            snprintf(b, sizeof b, "Wavelet basis with max frequency=%g would exceed the Nyquist frequency=%g. Try reducing the number of frequency bins.", fmax, nyq);
+            set_error(b);
+            return AMTFEAT_ERR_INVALID;
+        }
+        auto eds_of = [&](double cutoff) {
+            int c1 = std::max(0, (int)(std::ceil(std::log2(nyq / cutoff)) - 1) - 1);
+            int c2 = std::max(0, num_two_factors(c.hop_length) - p.n_oct + 1);
+            return std::min(c1, c2);
+        };
+        hi.eds_ref = eds_of(cutoff_ref);
+        hi.eds_lib = eds_of(cutoff_lib);
+        p.harm.push_back(hi);
+        const int eds = hi.eds_lib;
+        const double sr_post = sr0 / std::ldexp(1.0, eds);
+        if (eds + p.n_oct > kMaxLevels) { set_error("too many ladder levels"); return AMTFEAT_ERR_INVALID; }
+        p.n_levels = std::max(p.n_levels, eds + p.n_oct);
+        for (int i = 0; i < p.n_oct; ++i) {
+            const int lo = std::max(0, n_bins - p.n_filters * (i + 1)), hi_bin = n_bins - p.n_filters * i;
+            const int level = eds + i;
+            const double my_sr = sr0 / std::ldexp(1.0, level);
+            double max_len = 0;
+            std::vector<double> lens(hi_bin - lo);
+            for (int k = lo; k < hi_bin; ++k) {
+                lens[k - lo] = Q * my_sr / (freqs[k] + c.gamma / alpha_lib);
+                max_len = std::max(max_len, lens[k - lo]);
+            }
+            const int nfft = (int)std::ldexp(1.0, (int)std::ceil(std::log2(max_len)));
+            if (nfft < 32 || nfft > 2048) {
+                char b[160];
+                snprintf(b, sizeof b, "octave %d of harmonic %d needs n_fft=%d; supported range is 32..2048", i, h, nfft);
+                set_error(b);
+                return AMTFEAT_ERR_INVALID;
+            }
+            build_fft_tables(p, nfft);
+            const double oct_scale = std::sqrt(sr_post / my_sr);  // fft_basis *= sqrt(sr / my_sr)
+            for (int k = lo; k < hi_bin; ++k) {
+                const double ilen = lens[k - lo];
+                // n = arange(-ilen // 2, ilen // 2): floor(-ilen/2) .. floor(ilen/2) - 1
+                const long n0 = (long)std::floor(-ilen / 2.0), n1 = (long)std::floor(ilen / 2.0);
+                const int m = (int)(n1 - n0);
+                std::vector<std::complex<double>> sig(m);
+                double l1 = 0;
+                for (int j = 0; j < m; ++j) {
+                    double ph = (double)(n0 + j) * 2.0 * kPi * freqs[k] / my_sr;
+                    double w = m == 1 ? 1.0 : 0.5 - 0.5 * std::cos(2.0 * kPi * (double)j / (double)m);
+                    sig[j] = std::complex<double>(std::cos(ph), std::sin(ph)) * w;
+                    l1 += std::abs(sig[j]);
+                }
+                std::vector<std::complex<double>> a(nfft, 0.0);
+                const int lpad = (nfft - m) / 2;
+                const double renorm = ilen / (double)nfft;  // basis *= lengths / n_fft
+                for (int j = 0; j < m; ++j) {
+                    std::complex<double> v = sig[j] / l1;
+                    std::complex<float> v32((float)v.real(), (float)v.imag());           // dtype=complex64
+                    std::complex<double> s = std::complex<double>(v32.real(), v32.imag()) * renorm;
+                    a[lpad + j] = std::complex<double>((float)s.real(), (float)s.imag());  // stays complex64
+                }
+                fft_inplace(a);
+                const int nb = nfft / 2 + 1;
+                // sparsify_rows(quantile = 0.01)
+                std::vector<double> mags(nb);
+                double norm = 0;
+                for (int q = 0; q < nb; ++q) {
+                    a[q] = std::complex<double>((float)a[q].real(), (float)a[q].imag());
+                    mags[q] = std::abs(a[q]);
+                    norm += mags[q];
+                }
+                std::vector<double> srt(mags);
+                std::sort(srt.begin(), srt.end());
+                double cum = 0, thr = srt.back();
+                for (int q = 0; q < nb; ++q) {
+                    cum += srt[q] / norm;
+                    if (!(cum < 0.01)) { thr = srt[q]; break; }
+                }
+                int first = -1, last = -1;
+                for (int q = 0; q < nb; ++q)
+                    if (mags[q] >= thr) { if (first < 0) first = q; last = q; }
+                CqtRow row;
+                row.chan = h;
+                row.bin = k;
+                const double len_post = Q * sr_post / (freqs[k] + c.gamma / alpha_lib);  // lengths at the post-eds rate
+                row.inv_len = (float)(1.0 / len_post);
+                row.col0 = first;
+                row.cnt = last - first + 1;
+                row.woff = (int32_t)p.weights.size();
+                for (int q = first; q <= last; ++q) {
+                    std::complex<double> w = mags[q] >= thr ? a[q] * oct_scale : std::complex<double>(0, 0);
+                    p.weights.push_back({(float)w.real(), (float)w.imag()});
+                }
+                groups[{nfft, level}].push_back(row);
+            }
+        }
+    }
+    p.rows.clear();
+    p.items.clear();
+    for (auto &g : groups) {
+        CqtItem it{};
+        it.nfft = g.first.first;
+        it.level = g.first.second;
+        it.hop = c.hop_length >> it.level;
+        it.row0 = (int32_t)p.rows.size();
+        it.nrows = (int32_t)g.second.size();
+        it.kmin = INT32_MAX;
+        it.kmax = 0;
+        for (const CqtRow &rw : g.second) {
+            it.kmin = std::min(it.kmin, rw.col0);
+            it.kmax = std::max(it.kmax, rw.col0 + rw.cnt - 1);
+            p.rows.push_back(rw);
+        }
+        p.items.push_back(it);
+    }
+    return AMTFEAT_OK;
+}
+
+int build_plan_tables(Plan &p) {
+    amtfeat_config &c = p.cfg;
+    if (c.hop_length <= 0) { set_error("hop_length must be a positive integer"); return AMTFEAT_ERR_INVALID; }
+    if (!(c.sample_rate > 0)) { set_error("sample_rate must be positive"); return AMTFEAT_ERR_INVALID; }
+    switch (c.kind) {
+        case AMTFEAT_WAVEFORM:
+        case AMTFEAT_POWER:
+            if (c.win_length <= 0) { set_error("win_length must be positive"); return AMTFEAT_ERR_INVALID; }
+            p.C = 1;
+            p.F = c.kind == AMTFEAT_POWER ? 1 : c.win_length;
+            return AMTFEAT_OK;
+        case AMTFEAT_STFT:
+        case AMTFEAT_MEL:
+            if (!is_pow2(c.n_fft) || c.n_fft < 32 || c.n_fft > 2048) {
+                set_error("n_fft must be a power of two in [32, 2048]");
+                return AMTFEAT_ERR_INVALID;
+            }
+            if (c.win_length <= 0 || c.win_length > c.n_fft) { set_error("win_length must be in [1, n_fft]"); return AMTFEAT_ERR_INVALID; }
+            p.C = 1;
+            build_window(p);
+            build_fft_tables(p, c.n_fft);
+            if (c.kind == AMTFEAT_MEL) {
+                if (c.n_mels <= 0) { set_error("n_mels must be positive"); return AMTFEAT_ERR_INVALID; }
+                build_mel(p);
+                p.F = c.n_mels;
+            } else {
+                p.F = c.n_fft / 2 + 1;
+            }
+            return AMTFEAT_OK;
+        case AMTFEAT_VQT:
+        case AMTFEAT_HVQT:
+            if (c.n_harmonics < 1 || c.n_harmonics > AMTFEAT_MAX_HARMONICS) { set_error("n_harmonics out of range"); return AMTFEAT_ERR_INVALID; }
+            p.C = c.n_harmonics;
+            p.F = c.n_bins;
+            return build_vqt(p);
+        default:
+            set_error("unknown module kind");
+            return AMTFEAT_ERR_INVALID;
+    }
+}
+
+std::string describe(const Plan &p) {
+    const amtfeat_config &c = p.cfg;
+    std::ostringstream o;
+    o << "{\"kind\": " << c.kind << ", \"channels\": " << p.C << ", \"feature_size\": " << p.F << ", \"device\": " << p.device;
+    if (c.kind == AMTFEAT_MEL) o << ", \"mel_nnz\": " << p.mel_w.size();
+    if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
+        o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size()
+          << ", \"basis_nnz\": " << p.weights.size() << ", \"eds_ref\": [";
+        for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_ref;
+        o << "], \"eds_lib\": [";
+        for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_lib;
+        o << "], \"items\": [";
+        for (size_t i = 0; i < p.items.size(); ++i) {
+            const CqtItem &it = p.items[i];
+            o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
+              << ", \"rows\": " << it.nrows << ", \"kmin\": " << it.kmin << ", \"kmax\": " << it.kmax << "}";
+        }
+        o << "]";
+    }
+    o << "}";
+    return o.str();
+}
+
+}  // namespace amtfeat

@@ -1,0 +1,724 @@
+// sm_100a kernels of libamtfeat and their launchers.
+//
+//   K1/K2/K3  stft_kernel<NC, MODE>   frame + window + real FFT + |.|^2 (+ mel projection) + per-clip max
+//   K4        decimate_kernel         2:1 polyphase FIR decimator (soxr-HQ-class taps, x sqrt(2))
+//   K1/K5     cqt_kernel<NC>          rectangular-window FFT of ladder frames + sparse complex basis
+//                                     projection, shared by every harmonic that uses the same (level, n_fft)
+//   K6        db_epilogue_kernel      (x - ref_dB) floor -80, /80 + 1
+//   K7        power_kernel            SignalPower;  frames_kernel: WaveformWrapper framing
+//
+// All FFT kernels: 8 warps per CTA, one warp per 1024-complex-point unit (fft_device.cuh), audio tile
+// staged once in shared memory, outputs transposed through shared memory so global stores are
+// T-contiguous.  FP32 SIMT throughout (no tensor cores: the projections are sparse).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fft_device.cuh"
+#include "plan.h"
+
+namespace amtfeat {
+
+#define AMT_CUDA(call)                                                                                 \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+            return AMTFEAT_ERR_CUDA;                                                                   \
+        }                                                                                              \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// shared helpers (device)
+// ------------------------------------------------------------------------------------------------
+
+// Stage the samples needed by TT consecutive frames of one clip into shared memory, zero-filling
+// everything outside [0, n) (this realises centre padding / frame padding without a padded copy).
+// Overlapping frames (hop <= nfft): one contiguous span, float4 loads; frame f starts at shift + f * hop.
+// Disjoint frames (hop > nfft): TT separate segments, frame f starts at f * nfft (shift = 0).
+__device__ __forceinline__ void load_tile(float *tile, const float *__restrict__ src, long long n, long long s0, int hop,
+                                          int nfft, int TT, int tid, int &shift, int &fstride) {
+    if (hop <= nfft) {
+        fstride = hop;
+        shift = (int)(((s0 % 4) + 4) % 4);
+        const long long a0 = s0 - shift;
+        const int span = (TT - 1) * hop + nfft + shift;
+        const int nvec = (span + 3) >> 2;
+        float4 *tile4 = reinterpret_cast<float4 *>(tile);
+        for (int i = tid; i < nvec; i += kThreads) {
+            const long long g = a0 + 4ll * i;
+            float4 v;
+            if (g >= 0 && g + 3 < n) {
+                v = __ldg(reinterpret_cast<const float4 *>(src + g));
+            } else {
+                v.x = (g >= 0 && g < n) ? __ldg(src + g) : 0.f;
+                v.y = (g + 1 >= 0 && g + 1 < n) ? __ldg(src + g + 1) : 0.f;
+                v.z = (g + 2 >= 0 && g + 2 < n) ? __ldg(src + g + 2) : 0.f;
+                v.w = (g + 3 >= 0 && g + 3 < n) ? __ldg(src + g + 3) : 0.f;
+            }
+            tile4[i] = v;
+        }
+    } else {
+        fstride = nfft;
+        shift = 0;
+        const int total = TT * nfft;
+        for (int e = tid; e < total; e += kThreads) {
+            const int f = e / nfft, r = e - f * nfft;
+            const long long g = s0 + (long long)f * hop + r;
+            tile[e] = (g >= 0 && g < n) ? __ldg(src + g) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 + K3 : STFT / MelSpec
+// ------------------------------------------------------------------------------------------------
+
+struct StftParams {
+    const float *audio;
+    float *out;
+    const ClipMeta *meta;
+    float *maxbuf;
+    const float *window;
+    const float2 *tw1, *tw2;
+    const int *mel_start, *mel_cnt, *mel_off;
+    const float *mel_w;
+    int hop, pad, n_mels, decibels;
+    int tile_floats;
+};
+
+constexpr int MODE_STFT = 0, MODE_MEL = 1;
+
+template <int NC, int MODE>
+__global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
+    using L = FftLayout<NC>;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, PP = NC + 1, NFFT = 2 * NC;
+    extern __shared__ __align__(16) float smem[];
+    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                // NC
+    float2 *s_tw2 = s_tw1 + NC;                                      // NC/2 (k = 0 .. NC/2 - 1)
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC / 2);        // 8 * WARP_PITCH
+    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;            // tile_floats
+    float *s_stage = s_tile + p.tile_floats;                         // MEL: n_mels * (TT + 1)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int T = cm->T;
+    const int t0 = blockIdx.x * TT;
+    if (t0 >= T) return;
+
+    for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
+    for (int i = tid; i < NC / 2; i += kThreads) s_tw2[i] = p.tw2[i];
+    int shift, fstride;
+    load_tile(s_tile, p.audio + cm->in_off, cm->n, (long long)t0 * p.hop - p.pad, p.hop, NFFT, TT, tid, shift, fstride);
+    __syncthreads();
+
+    float2 *scr = reinterpret_cast<float2 *>(s_scr + warp * L::WARP_PITCH);
+    const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
+    const bool vec_ok = ((shift | fstride) & 1) == 0;
+    if (vec_ok) {
+        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+            const float2 x = *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+            const float2 w = __ldg(win2 + n);
+            return make_float2(x.x * w.x, x.y * w.y);
+        });
+    } else {
+        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+            const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
+            const float2 w = __ldg(win2 + n);
+            return make_float2(x[0] * w.x, x[1] * w.y);
+        });
+    }
+
+    // real-FFT split -> power spectrum, kept in this warp's scratch as P[g][0..NC]
+    {
+        float pw[16][2];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int q = lane + 32 * j;
+            const int g = q / (NC / 2), k = q % (NC / 2);
+            const float2 A = scr[g * S + k], B = scr[g * S + ((NC - k) & (NC - 1))];
+            float2 E, Tw;
+            rfft_split(A, B, s_tw2[k], E, Tw);
+            const float ax = E.x + Tw.x, ay = E.y + Tw.y, bx = E.x - Tw.x, by = E.y - Tw.y;
+            pw[j][0] = fmaf(ax, ax, ay * ay);
+            pw[j][1] = fmaf(bx, bx, by * by);
+        }
+        float pmid = 0.f;
+        if (lane < G) {
+            const float2 A = scr[lane * S + NC / 2];
+            pmid = fmaf(A.x, A.x, A.y * A.y);
+        }
+        __syncwarp();
+        float *P = reinterpret_cast<float *>(scr);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int q = lane + 32 * j;
+            const int g = q / (NC / 2), k = q % (NC / 2);
+            P[g * PP + k] = pw[j][0];
+            P[g * PP + NC - k] = pw[j][1];
+        }
+        if (lane < G) P[lane * PP + NC / 2] = pmid;
+        __syncwarp();
+    }
+
+    float vmax = 0.f;
+    float *out = p.out + cm->out_off;
+    if (MODE == MODE_MEL) {
+        const float *P = reinterpret_cast<const float *>(scr);
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            for (int m = lane; m < p.n_mels; m += 32) {
+                const int s = __ldg(p.mel_start + m), c = __ldg(p.mel_cnt + m);
+                const float *w = p.mel_w + __ldg(p.mel_off + m);
+                const float *pp = P + g * PP + s;
+                float acc = 0.f;
+                for (int j = 0; j < c; ++j) acc = fmaf(__ldg(w + j), pp[j], acc);
+                s_stage[m * (TT + 1) + warp * G + g] = acc;
+            }
+        }
+        __syncthreads();
+        const int total = p.n_mels * TT;
+        for (int idx = tid; idx < total; idx += kThreads) {
+            const int t = idx % TT, m = idx / TT;
+            if (t0 + t < T) {
+                const float v = s_stage[m * (TT + 1) + t];
+                vmax = fmaxf(vmax, v);
+                out[(long long)m * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : v;
+            }
+        }
+    } else {
+        __syncthreads();
+        constexpr int total = (NC + 1) * TT;
+        for (int idx = tid; idx < total; idx += kThreads) {
+            const int t = idx % TT, k = idx / TT;
+            if (t0 + t < T) {
+                const float v = s_scr[(t / G) * L::WARP_PITCH + (t % G) * PP + k];
+                vmax = fmaxf(vmax, v);
+                out[(long long)k * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v);
+            }
+        }
+    }
+    if (p.decibels) {
+        vmax = warp_max(vmax);
+        if (lane == 0) atomic_max_nonneg(p.maxbuf + blockIdx.y, vmax);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 : SignalPower (power.py:31-57) and WaveformWrapper framing (waveform.py:121-153)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads) power_kernel(const float *__restrict__ audio, float *__restrict__ out,
+                                                          const ClipMeta *__restrict__ meta, float *maxbuf, int hop, int win,
+                                                          int pad, int decibels) {
+    const ClipMeta cm = meta[blockIdx.y];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = blockIdx.x * kWarpsPerCta + warp;
+    if (t >= cm.T) return;
+    const float *src = audio + cm.in_off;
+    const long long s0 = (long long)t * hop - pad;
+    float acc = 0.f;
+    for (int i = lane; i < win; i += 32) {
+        const long long g = s0 + i;
+        const float x = (g >= 0 && g < cm.n) ? __ldg(src + g) : 0.f;
+        acc = fmaf(x, x, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float pw = acc / (float)win;
+        if (decibels) {
+            // amplitude_to_db applied to the power (power.py:55): 10 log10(max(1e-10, pw^2)) - ref
+            const float sq = pw * pw;
+            out[cm.out_off + t] = db10(fmaxf(1e-10f, sq));
+            atomic_max_nonneg(maxbuf + blockIdx.y, sq);
+        } else {
+            out[cm.out_off + t] = pw;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) frames_kernel(const float *__restrict__ audio, float *__restrict__ out,
+                                                           const ClipMeta *__restrict__ meta, int hop, int win, int pad) {
+    const ClipMeta cm = meta[blockIdx.z];
+    const int t = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (t >= cm.T || j >= win) return;
+    const long long g = (long long)t * hop - pad + j;
+    out[cm.out_off + (long long)j * cm.T + t] = (g >= 0 && g < cm.n) ? __ldg(audio + cm.in_off + g) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 : dB epilogue (common.py:199 + 224-225, mel.py:94, power.py:55)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict__ out, const ClipMeta *__restrict__ meta,
+                                                                const float *__restrict__ maxbuf, int C, int F, int scale01) {
+    const int seg = blockIdx.y, b = seg / C, c = seg % C;
+    const ClipMeta cm = meta[b];
+    const long long count = (long long)F * cm.T;
+    float *o = out + cm.out_off + (long long)c * count;
+    const float ref_db = db10(fmaxf(1e-10f, maxbuf[seg]));
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kThreads) {
+        float v = fmaxf(o[i] - ref_db, -80.0f);
+        if (scale01) v = v / 80.0f + 1.0f;
+        o[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 : 2:1 decimator.  y[m] = sum_k h[k] x[2m + D - k], D = (ntaps - 1) / 2 (even), zero extension,
+// h already scaled by sqrt(2) (librosa.resample(scale=True)).  Split into the two polyphase branches
+// so every shared-memory access is unit stride.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kDecTile = 1024;  // outputs per CTA
+constexpr int kDecR = kDecTile / kThreads;
+
+__global__ void __launch_bounds__(kThreads) decimate_kernel(const float *__restrict__ audio, float *__restrict__ ladder,
+                                                             const ClipMeta *__restrict__ meta, const float *__restrict__ taps,
+                                                             int ntaps, int level_out) {
+    extern __shared__ __align__(16) float smem[];
+    const ClipMeta *cm = meta + blockIdx.y;
+    const int len_out = cm->lvl_len[level_out], len_in = cm->lvl_len[level_out - 1];
+    const int m0 = blockIdx.x * kDecTile;
+    if (m0 >= len_out) return;
+    const float *src = (level_out == 1 ? audio : ladder) + cm->lvl_off[level_out - 1];
+    float *dst = ladder + cm->lvl_off[level_out];
+    const int D = (ntaps - 1) / 2, ne = kDecTile + D, nhe = D + 1, nho = D;
+    float *xe = smem, *xo = xe + ne + 16, *he = xo + ne, *ho = he + nhe;
+    const long long base = 2ll * m0 - D;  // even
+    for (int i = threadIdx.x; i < 2 * ne; i += kThreads) {
+        const long long g = base + i;
+        const float v = (g >= 0 && g < len_in) ? __ldg(src + g) : 0.f;
+        ((i & 1) ? xo : xe)[i >> 1] = v;
+    }
+    for (int i = threadIdx.x; i < ntaps; i += kThreads) ((i & 1) ? ho : he)[i >> 1] = __ldg(taps + i);
+    __syncthreads();
+    float acc[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) acc[r] = 0.f;
+    const int mm = threadIdx.x;
+    for (int j = 0; j < nhe; ++j) {
+        const float h = he[j];
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) acc[r] = fmaf(h, xe[mm + kThreads * r + D - j], acc[r]);
+    }
+    for (int j = 0; j < nho; ++j) {
+        const float h = ho[j];
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) acc[r] = fmaf(h, xo[mm + kThreads * r + D - j - 1], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) {
+        const int m = m0 + mm + kThreads * r;
+        if (m < len_out) dst[m] = acc[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K5 : CQT / VQT / HCQT response of one (ladder level, n_fft) item
+// ------------------------------------------------------------------------------------------------
+
+struct CqtParams {
+    const float *audio, *ladder;
+    float *out;
+    const ClipMeta *meta;
+    float *maxbuf;
+    const CqtItem *items;
+    const CqtRow *rows;
+    const float2 *weights;
+    const float2 *tw1, *tw2;
+    int C, F, decibels, tile_floats, stage_rows;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
+    using L = FftLayout<NC>;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, NFFT = 2 * NC;
+    constexpr int WP2 = L::WARP_PITCH / 2;  // warp pitch in float2
+    extern __shared__ __align__(16) float smem[];
+    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
+    float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH
+    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // tile_floats
+    float *s_stage = s_tile + p.tile_floats;                          // stage_rows * (TT + 1)
+    __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int T = cm->T;
+    const int t0 = blockIdx.x * TT;
+    if (t0 >= T) return;
+    const CqtItem it = p.items[blockIdx.z];
+
+    for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
+    for (int i = tid; i <= NC; i += kThreads) s_tw2[i] = p.tw2[i];
+    if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
+    const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
+    int shift, fstride;
+    load_tile(s_tile, src, cm->lvl_len[it.level], (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
+    __syncthreads();
+
+    float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
+    const bool vec_ok = ((shift | fstride) & 1) == 0;
+    if (vec_ok) {
+        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+            return *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+        });
+    } else {
+        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+            const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
+            return make_float2(x[0], x[1]);
+        });
+    }
+
+    // real-FFT split restricted to the band [kmin, kmax] any row of this item touches -> D[g][k - kmin]
+    const int kb = it.kmax - it.kmin + 1;
+    {
+        constexpr int JMAX = (G * (NC + 1) + 31) / 32;
+        float2 X[JMAX];
+        const int nband = G * kb;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int q = lane + 32 * j;
+            if (q < nband) {
+                const int g = q / kb, k = it.kmin + (q - g * kb);
+                const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
+                float2 E, Tw;
+                rfft_split(A, B, s_tw2[k], E, Tw);
+                X[j] = make_float2(E.x + Tw.x, E.y + Tw.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int q = lane + 32 * j;
+            if (q < nband) {
+                const int g = q / kb;
+                scr[g * S + (q - g * kb)] = X[j];
+            }
+        }
+    }
+    __syncthreads();
+
+    // sparse complex projection: one thread per (row, chunk of 8 frames)
+    const float2 *D = reinterpret_cast<const float2 *>(s_scr);
+    float *out = p.out + cm->out_off;
+    for (int rc = 0; rc < it.nrows; rc += p.stage_rows) {
+        const int nr = min(p.stage_rows, it.nrows - rc);
+        for (int w = tid; w < nr * G; w += kThreads) {
+            const int rl = w % nr, ch = w / nr;
+            const CqtRow row = p.rows[it.row0 + rc + rl];
+            const float2 *wts = p.weights + row.woff;
+            const int cbase = row.col0 - it.kmin;
+            float2 acc[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[f] = make_float2(0.f, 0.f);
+            for (int j = 0; j < row.cnt; ++j) {
+                const float2 wv = __ldg(wts + j);
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    const int t = ch * 8 + f;
+                    const float2 d = D[(t / G) * WP2 + (t % G) * S + cbase + j];
+                    acc[f].x = fmaf(wv.x, d.x, acc[f].x);
+                    acc[f].x = fmaf(-wv.y, d.y, acc[f].x);
+                    acc[f].y = fmaf(wv.x, d.y, acc[f].y);
+                    acc[f].y = fmaf(wv.y, d.x, acc[f].y);
+                }
+            }
+            float vmax = 0.f;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+                const float pw = fmaf(acc[f].x, acc[f].x, acc[f].y * acc[f].y) * row.inv_len;
+                if (t0 + ch * 8 + f < T) vmax = fmaxf(vmax, pw);
+                s_stage[rl * (TT + 1) + ch * 8 + f] = p.decibels ? db10(fmaxf(1e-10f, pw)) : sqrtf(pw);
+            }
+            if (p.decibels) atomicMax(&s_max[row.chan], __float_as_int(vmax));
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nr * TT; idx += kThreads) {
+            const int t = idx % TT, rl = idx / TT;
+            if (t0 + t < T) {
+                const CqtRow *row = p.rows + it.row0 + rc + rl;
+                out[((long long)__ldg(&row->chan) * p.F + __ldg(&row->bin)) * T + t0 + t] = s_stage[rl * (TT + 1) + t];
+            }
+        }
+        __syncthreads();
+    }
+    if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: upload, workspace layout, launch
+// ------------------------------------------------------------------------------------------------
+
+template <typename Tp> static int upload_vec(Plan &p, const std::vector<Tp> &h, Tp **d) {
+    *d = nullptr;
+    if (h.empty()) return AMTFEAT_OK;
+    AMT_CUDA(cudaMalloc(reinterpret_cast<void **>(d), h.size() * sizeof(Tp)));
+    p.d_allocs.push_back(*d);
+    AMT_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    return AMTFEAT_OK;
+}
+
+template <int NC> static size_t stft_smem(int tile_floats, int n_mels, bool mel) {
+    using L = FftLayout<NC>;
+    size_t fl = 2 * NC + NC + (size_t)kWarpsPerCta * L::WARP_PITCH + tile_floats;
+    if (mel) fl += (size_t)n_mels * (kWarpsPerCta * L::G + 1);
+    return fl * sizeof(float);
+}
+template <int NC> static size_t cqt_smem(int tile_floats, int stage_rows) {
+    using L = FftLayout<NC>;
+    size_t fl = 2 * NC + 2 * (NC + 2) + (size_t)kWarpsPerCta * L::WARP_PITCH + tile_floats +
+                (size_t)stage_rows * (kWarpsPerCta * L::G + 1);
+    return fl * sizeof(float);
+}
+static int tile_floats_for(int TT, int hop, int nfft) {
+    int fl = hop <= nfft ? (TT - 1) * hop + nfft + 8 : TT * nfft;
+    return (fl + 3) / 4 * 4;
+}
+
+template <int NC> static int set_attrs() {
+    AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(cqt_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return AMTFEAT_OK;
+}
+
+int upload_plan(Plan &p) {
+    AMT_CUDA(cudaSetDevice(p.device));
+    int rc;
+    if ((rc = set_attrs<1024>()) || (rc = set_attrs<512>()) || (rc = set_attrs<256>()) || (rc = set_attrs<128>()) ||
+        (rc = set_attrs<64>()) || (rc = set_attrs<32>()) || (rc = set_attrs<16>()))
+        return rc;
+    AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
+    if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
+    if ((rc = upload_vec(p, p.mel_cnt, &p.d_mel_cnt))) return rc;
+    if ((rc = upload_vec(p, p.mel_off, &p.d_mel_off))) return rc;
+    if ((rc = upload_vec(p, p.mel_w, &p.d_mel_w))) return rc;
+    if ((rc = upload_vec(p, p.taps, &p.d_taps))) return rc;
+    if ((rc = upload_vec(p, p.rows, &p.d_rows))) return rc;
+    if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
+    if ((rc = upload_vec(p, p.items, &p.d_items))) return rc;
+    for (auto &kv : p.fft) {
+        if ((rc = upload_vec(p, kv.second.tw1, &kv.second.d_tw1))) return rc;
+        if ((rc = upload_vec(p, kv.second.tw2, &kv.second.d_tw2))) return rc;
+    }
+    return AMTFEAT_OK;
+}
+
+void free_plan_device(Plan &p) {
+    if (p.device >= 0 && !p.d_allocs.empty()) {
+        cudaSetDevice(p.device);
+        for (void *d : p.d_allocs) cudaFree(d);
+    }
+    p.d_allocs.clear();
+}
+
+static bool is_vqt_kind(const Plan &p) { return p.cfg.kind == AMTFEAT_VQT || p.cfg.kind == AMTFEAT_HVQT; }
+
+// workspace: [ClipMeta x B][maxbuf float x B*C][ladder levels 1..n_levels-1]
+struct WsLayout {
+    size_t meta_off = 0, max_off = 0, ladder_off = 0, total = 0;
+};
+static WsLayout ws_layout(const Plan &p, int batch, const int64_t *n, std::vector<ClipMeta> *metas) {
+    WsLayout w;
+    w.meta_off = 0;
+    w.max_off = align_up((size_t)batch * sizeof(ClipMeta), 256);
+    w.ladder_off = align_up(w.max_off + (size_t)batch * p.C * sizeof(float), 256);
+    size_t ladder_elems = 0;
+    if (metas) metas->assign(batch, ClipMeta{});
+    if (is_vqt_kind(p)) {
+        for (int l = 1; l < p.n_levels; ++l)
+            for (int b = 0; b < batch; ++b) {
+                int32_t len[kMaxLevels];
+                level_lengths(p, n[b], len);
+                if (metas) {
+                    (*metas)[b].lvl_off[l] = (int64_t)ladder_elems;
+                    (*metas)[b].lvl_len[l] = len[l];
+                }
+                ladder_elems += align_up((size_t)len[l], 4);
+            }
+    }
+    w.total = w.ladder_off + ladder_elems * sizeof(float) + 256;
+    return w;
+}
+
+size_t workspace_bytes(const Plan &p, int batch, const int64_t *n) { return ws_layout(p, batch, n, nullptr).total; }
+
+int launch_count(const Plan &p, int batch, const int64_t *n) {
+    (void)batch;
+    (void)n;
+    int k = 0;
+    if (is_vqt_kind(p)) {
+        k += p.n_levels - 1;
+        int last = -1;
+        for (const CqtItem &it : p.items)
+            if (it.nfft != last) { ++k; last = it.nfft; }
+    } else {
+        k += 1;
+    }
+    if (p.cfg.decibels && p.cfg.kind != AMTFEAT_WAVEFORM) k += 1;
+    return k;
+}
+
+template <int NC>
+static int launch_stft(const Plan &p, const StftParams &sp, int batch, int maxT, cudaStream_t st) {
+    using L = FftLayout<NC>;
+    const int TT = kWarpsPerCta * L::G;
+    const bool mel = p.cfg.kind == AMTFEAT_MEL;
+    const size_t smem = stft_smem<NC>(sp.tile_floats, sp.n_mels, mel);
+    if (smem > 227 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+    dim3 grid((maxT + TT - 1) / TT, batch);
+    if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);
+    else stft_kernel<NC, MODE_STFT><<<grid, kThreads, smem, st>>>(sp);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
+template <int NC>
+static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int batch, int maxT, cudaStream_t st) {
+    using L = FftLayout<NC>;
+    const int TT = kWarpsPerCta * L::G;
+    int maxhop = 0, maxrows = 0;
+    for (int i = item0; i < item0 + nitems; ++i) {
+        maxhop = std::max(maxhop, p.items[i].hop);
+        maxrows = std::max(maxrows, p.items[i].nrows);
+    }
+    cp.tile_floats = tile_floats_for(TT, maxhop, 2 * NC);
+    cp.stage_rows = std::max(1, std::min(maxrows, 3072 / (TT + 1)));
+    cp.items = p.d_items + item0;
+    const FftTables &ft = p.fft.at(NC);
+    cp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1);
+    cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
+    const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
+    if (smem > 227 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+    dim3 grid((maxT + TT - 1) / TT, batch, nitems);
+    cqt_kernel<NC><<<grid, kThreads, smem, st>>>(cp);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
+int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
+            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream) {
+    if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
+    if (batch <= 0) return AMTFEAT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const amtfeat_config &c = p.cfg;
+    std::vector<ClipMeta> metas;
+    const WsLayout w = ws_layout(p, batch, n, &metas);
+    if (ws_bytes < w.total) { set_error("workspace too small"); return AMTFEAT_ERR_WORKSPACE; }
+    int maxT = 0;
+    int64_t maxn = 0;
+    for (int b = 0; b < batch; ++b) {
+        const int64_t T = output_frames(p, n[b]);
+        if (T < 0) { set_error("input too short for an uncentered frame (n_fft / win_length larger than the padded signal)"); return AMTFEAT_ERR_INVALID; }
+        if (in_off[b] % 4 != 0) { set_error("clip offsets must be multiples of 4 elements"); return AMTFEAT_ERR_INVALID; }
+        metas[b].in_off = in_off[b];
+        metas[b].lvl_off[0] = in_off[b];
+        metas[b].lvl_len[0] = (int32_t)n[b];
+        metas[b].n = n[b];
+        metas[b].out_off = out_off[b];
+        metas[b].T = (int32_t)T;
+        maxT = std::max<int>(maxT, (int)T);
+        maxn = std::max(maxn, n[b]);
+    }
+    if (maxT == 0) return AMTFEAT_OK;
+    char *ws = static_cast<char *>(d_ws);
+    ClipMeta *d_meta = reinterpret_cast<ClipMeta *>(ws + w.meta_off);
+    float *d_max = reinterpret_cast<float *>(ws + w.max_off);
+    float *d_ladder = reinterpret_cast<float *>(ws + w.ladder_off);
+    AMT_CUDA(cudaMemcpyAsync(d_meta, metas.data(), metas.size() * sizeof(ClipMeta), cudaMemcpyHostToDevice, st));
+    if (c.decibels) AMT_CUDA(cudaMemsetAsync(d_max, 0, (size_t)batch * p.C * sizeof(float), st));
+    int rc = AMTFEAT_OK;
+    int scale01 = 1;
+
+    if (c.kind == AMTFEAT_STFT || c.kind == AMTFEAT_MEL) {
+        const int NC = c.n_fft / 2;
+        const FftTables &ft = p.fft.at(NC);
+        StftParams sp{};
+        sp.audio = d_audio; sp.out = d_out; sp.meta = d_meta; sp.maxbuf = d_max; sp.window = p.d_window;
+        sp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1); sp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
+        sp.mel_start = p.d_mel_start; sp.mel_cnt = p.d_mel_cnt; sp.mel_off = p.d_mel_off; sp.mel_w = p.d_mel_w;
+        sp.hop = c.hop_length; sp.pad = c.center ? c.n_fft / 2 : 0; sp.n_mels = c.n_mels; sp.decibels = c.decibels;
+        sp.tile_floats = tile_floats_for(kWarpsPerCta * (1024 / NC), c.hop_length, c.n_fft);
+        switch (NC) {
+            case 1024: rc = launch_stft<1024>(p, sp, batch, maxT, st); break;
+            case 512: rc = launch_stft<512>(p, sp, batch, maxT, st); break;
+            case 256: rc = launch_stft<256>(p, sp, batch, maxT, st); break;
+            case 128: rc = launch_stft<128>(p, sp, batch, maxT, st); break;
+            case 64: rc = launch_stft<64>(p, sp, batch, maxT, st); break;
+            case 32: rc = launch_stft<32>(p, sp, batch, maxT, st); break;
+            default: rc = launch_stft<16>(p, sp, batch, maxT, st); break;
+        }
+        if (rc) return rc;
+    } else if (c.kind == AMTFEAT_POWER) {
+        dim3 grid((maxT + kWarpsPerCta - 1) / kWarpsPerCta, batch);
+        power_kernel<<<grid, kThreads, 0, st>>>(d_audio, d_out, d_meta, d_max, c.hop_length, c.win_length,
+                                                c.center ? c.win_length / 2 : 0, c.decibels);
+        AMT_CUDA(cudaGetLastError());
+        scale01 = 0;
+    } else if (c.kind == AMTFEAT_WAVEFORM) {
+        dim3 grid((maxT + 31) / 32, (c.win_length + 7) / 8, batch);
+        frames_kernel<<<grid, kThreads, 0, st>>>(d_audio, d_out, d_meta, c.hop_length, c.win_length,
+                                                 c.center ? c.win_length / 2 : 0);
+        AMT_CUDA(cudaGetLastError());
+        return AMTFEAT_OK;
+    } else {
+        // decimation ladder (levels 1 .. n_levels-1), then one launch per distinct n_fft
+        const int ntaps = (int)p.taps.size(), D = (ntaps - 1) / 2;
+        const size_t dsmem = (size_t)(2 * (kDecTile + D) + 16 + ntaps + 8) * sizeof(float);
+        int64_t len = maxn;
+        for (int l = 1; l < p.n_levels; ++l) {
+            len = (len + 1) / 2;
+            dim3 grid((unsigned)((len + kDecTile - 1) / kDecTile), batch);
+            decimate_kernel<<<grid, kThreads, dsmem, st>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
+            AMT_CUDA(cudaGetLastError());
+        }
+        CqtParams cp{};
+        cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
+        cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
+        cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
+        size_t i0 = 0;
+        while (i0 < p.items.size()) {
+            size_t i1 = i0;
+            while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft) ++i1;
+            const int NC = p.items[i0].nfft / 2, cnt = (int)(i1 - i0);
+            switch (NC) {
+                case 1024: rc = launch_cqt<1024>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 512: rc = launch_cqt<512>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 256: rc = launch_cqt<256>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 128: rc = launch_cqt<128>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 64: rc = launch_cqt<64>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 32: rc = launch_cqt<32>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                default: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+            }
+            if (rc) return rc;
+            i0 = i1;
+        }
+    }
+    if (c.decibels) {
+        int64_t maxcount = (int64_t)p.F * maxT;
+        unsigned gx = (unsigned)std::min<int64_t>(1024, (maxcount + kThreads * 4 - 1) / (kThreads * 4));
+        dim3 grid(std::max(1u, gx), batch * p.C);
+        db_epilogue_kernel<<<grid, kThreads, 0, st>>>(d_out, d_meta, d_max, p.C, p.F, scale01);
+        AMT_CUDA(cudaGetLastError());
+    }
+    return AMTFEAT_OK;
+}
+
+}  // namespace amtfeat

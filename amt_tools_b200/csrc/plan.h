@@ -1,0 +1,107 @@
+// Internal plan representation shared by the host-side table builder (host_plan.cpp), the kernel
+// launchers (kernels_*.cu) and the C-ABI (api.cpp).  Not part of the public interface.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/amtfeat.h"
+
+namespace amtfeat {
+
+constexpr int kMaxLevels = 16;      // ladder depth (octaves + early downsampling)
+constexpr int kWarpsPerCta = 8;     // every FFT kernel runs 8 warps, one "unit" (1024 complex points) each
+constexpr int kThreads = kWarpsPerCta * 32;
+
+struct cfloat {
+    float x, y;
+};
+
+// Per-clip launch metadata (device array, one per clip of the batch).
+struct ClipMeta {
+    int64_t in_off;                 // element offset of the clip inside d_audio
+    int64_t n;                      // samples
+    int64_t out_off;                // element offset of the clip's (C, F, T) block inside d_out
+    int64_t lvl_off[kMaxLevels];    // level 0: == in_off (d_audio); level >= 1: offset inside the ladder buffer
+    int32_t lvl_len[kMaxLevels];    // samples at each ladder level
+    int32_t T;                      // output frames
+    int32_t pad_;
+};
+
+// One row of a sparsified frequency-domain wavelet basis (librosa __vqt_filter_fft + sparsify_rows).
+struct CqtRow {
+    int32_t chan;      // output channel (harmonic index)
+    int32_t bin;       // output frequency bin
+    float inv_len;     // 1 / length (the `V /= sqrt(lengths)` of librosa.vqt, squared, applied to power)
+    int32_t col0;      // first kept FFT bin
+    int32_t cnt;       // kept band width (dropped entries inside the band are stored as zeros)
+    int32_t woff;      // offset into the weight array
+};
+
+// All rows that consume the FFT frames of one (ladder level, n_fft) pair.
+struct CqtItem {
+    int32_t level, nfft, hop, row0, nrows, kmin, kmax, pad_;
+};
+
+// FFT constant tables for one complex length NC = n_fft / 2.
+struct FftTables {
+    std::vector<cfloat> tw1;   // [k1][n2] = exp(-2 pi i k1 n2 / NC), inter-pass twiddles
+    std::vector<cfloat> tw2;   // [k] = exp(-i pi k / NC), k = 0..NC, real-FFT split twiddles
+    cfloat *d_tw1 = nullptr, *d_tw2 = nullptr;
+};
+
+struct HarmonicInfo {
+    double fmin;
+    int eds_ref;   // reference formula, vqt.py:64-100 (frame counts / sample ranges)
+    int eds_lib;   // librosa >= 0.10 formula (signal path)
+};
+
+struct Plan {
+    amtfeat_config cfg{};
+    int device = -1;
+    int C = 1, F = 1;
+
+    // STFT family
+    std::vector<float> window;                 // n_fft, periodic Hann of win_length, centre padded
+    std::vector<int32_t> mel_start, mel_cnt, mel_off;
+    std::vector<float> mel_w;
+
+    // VQT family
+    int n_oct = 0, n_filters = 0, n_levels = 0;
+    std::vector<HarmonicInfo> harm;
+    std::vector<float> taps;                   // 2:1 decimator, includes the sqrt(2) of `scale=True`
+    std::vector<CqtRow> rows;
+    std::vector<cfloat> weights;
+    std::vector<CqtItem> items;
+
+    std::map<int, FftTables> fft;              // keyed by NC
+
+    // device copies
+    float *d_window = nullptr, *d_mel_w = nullptr, *d_taps = nullptr;
+    int32_t *d_mel_start = nullptr, *d_mel_cnt = nullptr, *d_mel_off = nullptr;
+    CqtRow *d_rows = nullptr;
+    cfloat *d_weights = nullptr;
+    CqtItem *d_items = nullptr;                // sorted by nfft so each kernel instantiation sees a contiguous slice
+    std::vector<void *> d_allocs;
+};
+
+// ---- host_plan.cpp ----
+void set_error(const std::string &msg);
+int build_plan_tables(Plan &p);                 // fills every host table, validates the configuration
+int64_t expected_frames(const Plan &p, int64_t n);
+int64_t output_frames(const Plan &p, int64_t n);
+void level_lengths(const Plan &p, int64_t n, int32_t *len /* kMaxLevels */);
+int sample_range(const Plan &p, int64_t frames, int64_t *lo, int64_t *hi);
+std::string describe(const Plan &p);
+
+// ---- kernels_*.cu ----
+int upload_plan(Plan &p);
+void free_plan_device(Plan &p);
+size_t workspace_bytes(const Plan &p, int batch, const int64_t *n);
+int launch_count(const Plan &p, int batch, const int64_t *n);
+int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
+            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream);
+
+}  // namespace amtfeat

@@ -1,0 +1,146 @@
+/*
+ * libamtfeat -- C-ABI of the B200-native amt_tools.features front end.
+ *
+ * The reference (cwitkowitz/amt-tools) has NO native / FFI interface: its boundary is the Python class
+ * API of amt_tools.features.FeatureModule.  Every entry point below therefore cites the reference
+ * *method* it replaces (paths under /root/reference/amt_tools/features/).  A maintainer binds these
+ * with ctypes; amt_tools_b200/_lib.py is that binding.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (a stream is passed as void*, i.e. a
+ *     cudaStream_t / CUstream handle; NULL = legacy default stream).
+ *   - every function returns an int status (0 = AMTFEAT_OK) unless it returns a value that cannot
+ *     fail; on failure amtfeat_last_error() (thread-local) holds a message.  Nothing throws across
+ *     the ABI, nothing calls exit().
+ *   - a plan is immutable after creation: amtfeat_process* is re-entrant on distinct
+ *     (stream, workspace) pairs.  The caller owns audio, output and workspace buffers.
+ *   - device = -1 builds a host-only plan (all integer / time queries work, no GPU needed);
+ *     amtfeat_process* on such a plan fails with AMTFEAT_ERR_NO_DEVICE.  There is no CPU compute path.
+ */
+#ifndef AMTFEAT_H_
+#define AMTFEAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMTFEAT_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define AMTFEAT_API __attribute__((visibility("default")))
+#else
+#define AMTFEAT_API
+#endif
+
+enum {
+    AMTFEAT_OK = 0,
+    AMTFEAT_ERR_INVALID = 1,   /* bad argument / unsupported configuration (Python: ValueError)   */
+    AMTFEAT_ERR_CUDA = 2,      /* a CUDA runtime call failed                                       */
+    AMTFEAT_ERR_NO_DEVICE = 3, /* compute requested on a host-only plan                            */
+    AMTFEAT_ERR_WORKSPACE = 4  /* workspace too small                                              */
+};
+
+/* Which reference FeatureModule a plan mirrors. */
+enum {
+    AMTFEAT_WAVEFORM = 0, /* waveform.py:14  WaveformWrapper  -> (win, T) frames                   */
+    AMTFEAT_STFT = 1,     /* stft.py:11      STFT             -> (1, n_fft/2+1, T)                 */
+    AMTFEAT_MEL = 2,      /* mel.py:11       MelSpec          -> (1, n_mels, T)                    */
+    AMTFEAT_VQT = 3,      /* vqt.py:17 VQT / cqt.py:7 CQT (gamma = 0) -> (1, n_bins, T)            */
+    AMTFEAT_HVQT = 4,     /* hvqt.py:12 HVQT / hcqt.py:7 HCQT -> (H, n_bins, T), shared ladder     */
+    AMTFEAT_POWER = 5     /* power.py:12     SignalPower      -> (T,)                              */
+};
+
+#define AMTFEAT_MAX_HARMONICS 16
+
+/* Constructor arguments of the reference modules (stft.py:15, mel.py:15, vqt.py:21, hvqt.py:16,
+ * power.py:16, waveform.py:18), with the Python-side defaults already resolved. */
+typedef struct amtfeat_config {
+    int32_t kind;
+    int32_t hop_length;
+    double sample_rate;
+    int32_t decibels;       /* common.py:203-230 post_proc / power.py:52-55                         */
+    int32_t center;         /* waveform.py:41                                                        */
+    int32_t win_length;     /* waveform / stft / mel / power                                         */
+    int32_t n_fft;          /* stft / mel (power of two, 32..2048)                                   */
+    int32_t n_mels;         /* mel.py:37                                                             */
+    int32_t htk;            /* mel.py:38                                                             */
+    int32_t n_bins;         /* vqt.py:49                                                             */
+    int32_t bins_per_octave;
+    double fmin;            /* vqt.py:41-46 (already defaulted to note C1)                           */
+    double gamma;           /* vqt.py:52-58 (already defaulted); 0 for CQT / HCQT                    */
+    int32_t n_harmonics;    /* hvqt.py:38-42; 1 for VQT                                              */
+    int32_t n_decim_taps;   /* 0 = built-in soxr-HQ-class design; else length of decim_taps (odd)    */
+    double harmonics[AMTFEAT_MAX_HARMONICS]; /* sorted ascending (hvqt.py:40)                        */
+    const double *decim_taps; /* optional 2:1 decimator taps, DC gain 1, linear phase (may be NULL)  */
+} amtfeat_config;
+
+typedef struct amtfeat_plan amtfeat_plan;
+
+AMTFEAT_API int amtfeat_version(void);
+AMTFEAT_API const char *amtfeat_last_error(void);
+
+/* FeatureModule.__init__ of the kind named in cfg->kind.  device >= 0: CUDA ordinal; -1: host-only. */
+AMTFEAT_API int amtfeat_plan_create(const amtfeat_config *cfg, int device, amtfeat_plan **out);
+AMTFEAT_API void amtfeat_plan_destroy(amtfeat_plan *plan);
+
+/* get_expected_frames (common.py:41-66, waveform.py:43-66, vqt.py:102-134, hvqt.py:60-83). */
+AMTFEAT_API int64_t amtfeat_expected_frames(const amtfeat_plan *plan, int64_t num_samples);
+/* Frames process_audio actually returns for num_samples (what librosa would give; equals
+ * amtfeat_expected_frames for every configuration of the reference's examples). */
+AMTFEAT_API int64_t amtfeat_output_frames(const amtfeat_plan *plan, int64_t num_samples);
+/* get_sample_range (common.py:68-97, waveform.py:68-96, vqt.py:136-165, hvqt.py:85-105): the range is
+ * the inclusive interval [*lo, *hi]; num_frames <= 0 gives lo = hi = 0 (the reference's array([0])). */
+AMTFEAT_API int amtfeat_sample_range(const amtfeat_plan *plan, int64_t num_frames, int64_t *lo, int64_t *hi);
+/* get_num_samples_required (common.py:99-112). */
+AMTFEAT_API int64_t amtfeat_num_samples_required(const amtfeat_plan *plan);
+/* get_times (common.py:232-258, waveform.py:155-185, vqt.py:197-227, hvqt.py:148-168): writes
+ * amtfeat_expected_frames(num_samples) float64 values, bit-exact with librosa.frames_to_time. */
+AMTFEAT_API int amtfeat_times(const amtfeat_plan *plan, int64_t num_samples, int at_start, double *out, int64_t capacity);
+/* VQT.get_early_ds_count (vqt.py:64-100) for harmonic index h (0 for VQT / CQT). */
+AMTFEAT_API int amtfeat_early_ds_count(const amtfeat_plan *plan, int harmonic_index);
+/* get_num_channels / get_feature_size (common.py:284-308 and overrides). */
+AMTFEAT_API int amtfeat_num_channels(const amtfeat_plan *plan);
+AMTFEAT_API int amtfeat_feature_size(const amtfeat_plan *plan);
+/* Shape of process_audio's result for one clip: ndim in {1, 2, 3}; empty audio follows the
+ * reference quirks (stft.py:59 -> (1, n_fft, 0); mel.py:57; waveform.py:138). */
+AMTFEAT_API int amtfeat_out_shape(const amtfeat_plan *plan, int64_t num_samples, int64_t shape[3], int *ndim);
+/* JSON description of the plan (ladder levels, n_fft per level, nnz, taps, ...) for tests / docs. */
+AMTFEAT_API int amtfeat_plan_describe(const amtfeat_plan *plan, char *buf, size_t capacity);
+
+/* Device workspace needed by amtfeat_process for a batch with these clip lengths. */
+AMTFEAT_API size_t amtfeat_workspace_bytes(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
+
+/*
+ * process_audio (stft.py:42, mel.py:40, vqt.py:167, hvqt.py:107, power.py:31, waveform.py:121) for a
+ * ragged batch of clips, all on the device.
+ *   d_audio        device float32; clip b occupies [in_offsets[b], in_offsets[b] + num_samples[b])
+ *                  (element offsets, each a multiple of 4)
+ *   d_out          device float32; clip b's (C, F, T_b) block, T contiguous, starts at out_offsets[b]
+ *   in_offsets, num_samples, out_offsets   HOST arrays of length batch
+ *   d_workspace    device scratch of at least amtfeat_workspace_bytes(...)
+ * Work is enqueued on `stream`; the call does not synchronise.
+ */
+AMTFEAT_API int amtfeat_process(const amtfeat_plan *plan, const float *d_audio, const int64_t *in_offsets,
+                    const int64_t *num_samples, const int64_t *out_offsets, int batch, float *d_out,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Same, with HOST buffers (pinned for full PCIe speed): copies the audio to d_audio, runs
+ * amtfeat_process, copies the features back to h_out -- all stream-ordered on `stream`, no sync.
+ * d_audio / d_out are caller-provided device staging buffers large enough for the batch.
+ */
+AMTFEAT_API int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const int64_t *in_offsets,
+                         const int64_t *num_samples, const int64_t *out_offsets, int batch, float *h_out,
+                         int64_t audio_elems, int64_t out_elems, float *d_audio, float *d_out,
+                         void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Number of kernel launches amtfeat_process enqueues for this batch (bench.py's gpu_launches). */
+AMTFEAT_API int amtfeat_launch_count(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMTFEAT_H_ */
