@@ -165,4 +165,20 @@ int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const i
     return AMTFEAT_OK;
 }
 
+int amtfeat_profile_enable(amtfeat_plan *plan, int enable) {
+    if (!plan) return AMTFEAT_ERR_INVALID;
+    plan->p.prof_enabled = enable != 0;
+    return AMTFEAT_OK;
+}
+
+int amtfeat_profile_read(amtfeat_plan *plan, char *buf, size_t capacity) {
+    if (!plan) return AMTFEAT_ERR_INVALID;
+    std::string s;
+    int rc = amtfeat::profile_read(plan->p, s);
+    if (rc != AMTFEAT_OK) return rc;
+    if (s.size() + 1 > capacity) { amtfeat::set_error("profile buffer too small"); return AMTFEAT_ERR_INVALID; }
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return AMTFEAT_OK;
+}
+
 }  // extern "C"

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -494,7 +495,7 @@ static int tile_floats_for(int TT, int hop, int nfft) {
 template <int NC> static int set_attrs() {
     AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    AMT_CUDA(cudaFuncSetAttribute(cqt_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(cqt_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     return AMTFEAT_OK;
 }
 
@@ -521,6 +522,32 @@ int upload_plan(Plan &p) {
     return AMTFEAT_OK;
 }
 
+// Sums the recorded event pairs per kernel name into `json` and clears the records.
+int profile_read(const Plan &p, std::string &json) {
+    std::map<std::string, std::pair<double, int>> acc;
+    for (auto &r : p.prof) {
+        cudaEvent_t e0 = (cudaEvent_t)r.e0, e1 = (cudaEvent_t)r.e1;
+        AMT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        AMT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        acc[r.name].first += ms;
+        acc[r.name].second += 1;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    p.prof.clear();
+    json = "{";
+    bool first = true;
+    for (auto &kv : acc) {
+        char b[256];
+        snprintf(b, sizeof b, "%s\"%s\": {\"ms\": %.6f, \"launches\": %d}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        json += b;
+        first = false;
+    }
+    json += "}";
+    return AMTFEAT_OK;
+}
+
 void free_plan_device(Plan &p) {
     if (p.device >= 0 && !p.d_allocs.empty()) {
         cudaSetDevice(p.device);
@@ -528,6 +555,23 @@ void free_plan_device(Plan &p) {
     }
     p.d_allocs.clear();
 }
+
+struct ProfScope {
+    const Plan &p;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    ProfScope(const Plan &plan, const char *name, cudaStream_t s) : p(plan), st(s) {
+        if (!p.prof_enabled) return;
+        cudaEvent_t e0;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        p.prof.push_back({name, e0, e1});
+    }
+    ~ProfScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
 
 static bool is_vqt_kind(const Plan &p) { return p.cfg.kind == AMTFEAT_VQT || p.cfg.kind == AMTFEAT_HVQT; }
 
@@ -584,6 +628,7 @@ static int launch_stft(const Plan &p, const StftParams &sp, int batch, int maxT,
     const size_t smem = stft_smem<NC>(sp.tile_floats, sp.n_mels, mel);
     if (smem > 227 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
     dim3 grid((maxT + TT - 1) / TT, batch);
+    ProfScope ps(p, mel ? "stft_kernel_mel" : "stft_kernel_mag", st);
     if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);
     else stft_kernel<NC, MODE_STFT><<<grid, kThreads, smem, st>>>(sp);
     AMT_CUDA(cudaGetLastError());
@@ -606,8 +651,10 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     cp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1);
     cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
     const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
-    if (smem > 227 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+    if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
     dim3 grid((maxT + TT - 1) / TT, batch, nitems);
+    static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
+    ProfScope ps(p, nm.c_str(), st);
     cqt_kernel<NC><<<grid, kThreads, smem, st>>>(cp);
     AMT_CUDA(cudaGetLastError());
     return AMTFEAT_OK;
@@ -668,6 +715,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         if (rc) return rc;
     } else if (c.kind == AMTFEAT_POWER) {
         dim3 grid((maxT + kWarpsPerCta - 1) / kWarpsPerCta, batch);
+        ProfScope ps(p, "power_kernel", st);
         power_kernel<<<grid, kThreads, 0, st>>>(d_audio, d_out, d_meta, d_max, c.hop_length, c.win_length,
                                                 c.center ? c.win_length / 2 : 0, c.decibels);
         AMT_CUDA(cudaGetLastError());
@@ -686,6 +734,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
             dim3 grid((unsigned)((len + kDecTile - 1) / kDecTile), batch);
+            ProfScope ps(p, "decimate_kernel", st);
             decimate_kernel<<<grid, kThreads, dsmem, st>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
             AMT_CUDA(cudaGetLastError());
         }
@@ -715,6 +764,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         int64_t maxcount = (int64_t)p.F * maxT;
         unsigned gx = (unsigned)std::min<int64_t>(1024, (maxcount + kThreads * 4 - 1) / (kThreads * 4));
         dim3 grid(std::max(1u, gx), batch * p.C);
+        ProfScope ps(p, "db_epilogue_kernel", st);
         db_epilogue_kernel<<<grid, kThreads, 0, st>>>(d_out, d_meta, d_max, p.C, p.F, scale01);
         AMT_CUDA(cudaGetLastError());
     }

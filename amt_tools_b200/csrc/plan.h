@@ -85,6 +85,12 @@ struct Plan {
     cfloat *d_weights = nullptr;
     CqtItem *d_items = nullptr;                // sorted by nfft so each kernel instantiation sees a contiguous slice
     std::vector<void *> d_allocs;
+
+    // optional per-kernel timing (amtfeat_profile_*): CUDA event pairs recorded around every launch of
+    // amtfeat_process on the launching stream.  Not thread-safe; meant for bench.py only.
+    struct ProfRec { std::string name; void *e0, *e1; };
+    mutable bool prof_enabled = false;
+    mutable std::vector<ProfRec> prof;
 };
 
 // ---- host_plan.cpp ----
@@ -101,6 +107,7 @@ int upload_plan(Plan &p);
 void free_plan_device(Plan &p);
 size_t workspace_bytes(const Plan &p, int batch, const int64_t *n);
 int launch_count(const Plan &p, int batch, const int64_t *n);
+int profile_read(const Plan &p, std::string &json);
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
             int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream);
 

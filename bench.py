@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""
+bench.py -- audio-hours/sec of HCQT + log-mel features (BASELINE.json `metric`), one rank per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c4|c1] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic tracks that stays fixed per rank
+(weak scaling: every rank processes its own `--batch` tracks; no data-path collective).  Default workload
+`c5` is the configuration the metric is quoted on (BASELINE.json configs[4], per-GPU shape):
+HCQT(22050, hop 256, 360 bins @ 60 bpo, h = .5,1,2,3,4,5) + MelSpec(16000, n_fft 2048, hop 512, 229 mels)
+on 4-minute tracks.  `value` = device-resident throughput; `e2e` = the same through the C-ABI host entry
+point (pinned host audio in, pinned host features out, copies inside the timed region).
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: librosa itself cannot be
+installed here) on all host cores over a bounded sample of the same workload.
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'audio-hours/sec of HCQT+log-mel features'
+
+WORKLOADS = {
+    # name: (description, [(module ctor name, kwargs, sample_rate)], clip seconds, default batch per GPU)
+    'c5': ('HCQT(22050,hop256,360bins,60bpo,h=.5,1,2,3,4,5)+MelSpec(16000,2048,512,229) on 240 s tracks (configs[4] per-GPU shape)',
+           [('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), 22050),
+            ('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000)], 240.0, 4),
+    'c2': ('MelSpec(16000,2048,512,229) on 64 x 20 s clips (configs[1])',
+           [('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000)], 20.0, 64),
+    'c3': ('HCQT(22050,hop256,360bins,60bpo,6 harmonics) on 30 s clips (configs[2])',
+           [('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), 22050)], 30.0, 16),
+    'c4': ('STFT(2048,512)+VQT(84,12,gamma auto)+SignalPower @22050 on 240 s tracks (configs[3])',
+           [('STFT', dict(sample_rate=22050, hop_length=512, n_fft=2048), 22050),
+            ('VQT', dict(sample_rate=22050, hop_length=512), 22050),
+            ('SignalPower', dict(sample_rate=22050, hop_length=512), 22050)], 240.0, 4),
+    'c1': ('CQT(22050,hop512,192bins,24bpo) on one 30 s clip (configs[0])',
+           [('CQT', dict(sample_rate=22050, hop_length=512, n_bins=192, bins_per_octave=24), 22050)], 30.0, 1),
+}
+
+
+def synth_batch(sr, seconds, batch, seed0):
+    from amt_tools_b200.synth import piano_like
+    n = int(round(sr * seconds))
+    uniq = min(batch, 2)  # two distinct tracks, alternated: generation time stays bounded
+    tracks = [piano_like(n, sr, seed=seed0 + i) for i in range(uniq)]
+    return np.stack([tracks[i % uniq] for i in range(batch)])
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+
+def _oracle_modules(spec):
+    from oracle import modules as om
+    table = {'HCQT': om.OHCQT, 'MelSpec': om.OMelSpec, 'STFT': om.OSTFT, 'VQT': om.OVQT, 'CQT': om.OCQT,
+             'SignalPower': om.OSignalPower}
+    return [(table[name](dtype=np.float32, **kw), sr) for name, kw, sr in spec]
+
+
+_AUDIO_CACHE = {}
+
+
+def _oracle_worker(args):
+    wl, seconds, seed = args
+    from threadpoolctl import threadpool_limits
+    from amt_tools_b200.synth import piano_like
+    mods = _oracle_modules(WORKLOADS[wl][1])
+    for _, sr in mods:  # synthetic audio is generated once per worker process, outside the timed part
+        if (sr, seconds) not in _AUDIO_CACHE:
+            _AUDIO_CACHE[(sr, seconds)] = piano_like(int(round(sr * seconds)), sr, seed=seed)
+    with threadpool_limits(limits=1):
+        t = time.perf_counter()
+        for m, sr in mods:
+            m.process_audio(_AUDIO_CACHE[(sr, seconds)])
+        return time.perf_counter() - t
+
+
+def cpu_sample_seconds(wl):
+    # bounded sample of the same workload: short clips of the same modules (CPU cost is linear in duration)
+    return {'c5': 20.0, 'c3': 20.0, 'c4': 30.0, 'c2': 20.0, 'c1': 30.0}[wl]
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))  # one single-threaded oracle process per host core (capped)
+    sec = cpu_sample_seconds(args.workload)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs) as pool:
+        for _ in range(max(1, args.warmup)):
+            pool.map(_oracle_worker, [(args.workload, sec, 100 + i) for i in range(procs)], chunksize=1)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_oracle_worker, [(args.workload, sec, 1000 * s + i) for i in range(procs)], chunksize=1)
+        dt = time.perf_counter() - t0
+    hours = args.steps * procs * sec / 3600.0
+    value = hours / dt
+    wl = WORKLOADS[args.workload]
+    sample = '%d clips x %.0f s per step (one per process), oracle float32 port of the librosa algorithm' % (procs, sec)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'audio-hours/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload + ': ' + wl[0], 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'audio-hours/s', 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'audio-hours/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+
+class ClockSampler(object):
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(',')]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                out['sm_max_mhz'] = float(f[2])
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out['sm_mhz'] = float(np.median(sm))
+            out['samples'] = len(sm)
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def algorithmic_bytes(mod, n):
+    """4 * N_in + 4 * C * F * T_out per clip."""
+    T = mod.get_expected_frames(np.empty(n, dtype=np.float32))
+    return 4 * n + 4 * mod.get_num_channels() * mod.get_feature_size() * T
+
+
+def kernel_algorithmic_bytes(mod, name, n):
+    """
+    Algorithmic bytes ONE clip contributes to the kernel `name` (DESIGN.md "Kernels"): every input sample of the
+    signal(s) it frames read once + every output element it produces written once.
+    """
+    d = mod.describe()
+    T = mod.get_expected_frames(np.empty(n, dtype=np.float32))
+    if name.startswith('stft_kernel'):
+        return 4 * n + 4 * mod.get_feature_size() * T
+    if name.startswith('cqt_kernel_nfft'):
+        nfft = int(name[len('cqt_kernel_nfft'):])
+        total = 0
+        for it in d['items']:
+            if it['n_fft'] == nfft:
+                total += 4 * int(np.ceil(n / 2.0 ** it['level'])) + 4 * it['rows'] * T
+        return total
+    if name == 'decimate_kernel':
+        return sum(4 * int(np.ceil(n / 2.0 ** (l - 1))) + 4 * int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
+    if name == 'db_epilogue_kernel':
+        return 8 * mod.get_num_channels() * mod.get_feature_size() * T
+    if name == 'power_kernel':
+        return 4 * n + 4 * T
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import amt_tools_b200 as ab
+    from amt_tools_b200 import _lib
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; amt_tools_b200 has no CPU compute path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    desc, spec, seconds, default_batch = WORKLOADS[args.workload]
+    B = args.batch or default_batch
+    mods, dev_audio, host_audio = [], [], []
+    for i, (name, kw, sr) in enumerate(spec):
+        m = getattr(ab, name)(device=dev, **kw)
+        a = synth_batch(sr, seconds, B, seed0=5000 + 1000 * rank + 10 * i)
+        mods.append(m)
+        host_audio.append(torch.from_numpy(a).pin_memory())
+        dev_audio.append(host_audio[-1].to(dev))
+    n_per = [int(a.shape[1]) for a in host_audio]
+    hours_per_step = B * seconds / 3600.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        outs = []
+        for m, a in zip(mods, dev_audio):
+            outs.append(m.process_audio(a))
+        return outs
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for _ in range(max(args.warmup, 3)):
+        outs = step_device()
+    del outs
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for m in mods:
+        _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        outs = step_device()
+        del outs
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = {}
+    for m in mods:
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(_lib.lib.amtfeat_profile_read(m._dev_plan.handle, buf, len(buf)))
+        _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 0))
+        for k, v in json.loads(buf.value.decode()).items():
+            prof[(m.features_name(), k)] = v
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * args.steps * hours_per_step / (ms_total / 1e3)
+
+    # ---------------- end to end through the C-ABI host entry point ----------------
+    e2e = None
+    if not args.no_e2e:
+        # two pipeline slots so the copies of step i+1 overlap the kernels of step i
+        slots = []
+        for _ in range(2):
+            slot = []
+            for m, ha, n in zip(mods, host_audio, n_per):
+                shape = m._out_shape(n)
+                per = int(np.prod(shape))
+                n_arr = _lib.i64_array([n] * B)
+                ws_bytes = int(_lib.lib.amtfeat_workspace_bytes(m._dev_plan.handle, B, n_arr))
+                slot.append(dict(
+                    m=m, h_in=ha, n_arr=n_arr, in_off=_lib.i64_array([b * n for b in range(B)]),
+                    out_off=_lib.i64_array([b * per for b in range(B)]), per=per,
+                    h_out=torch.empty(B * per, dtype=torch.float32).pin_memory(),
+                    d_in=torch.empty(B * n, dtype=torch.float32, device=dev),
+                    d_out=torch.empty(B * per, dtype=torch.float32, device=dev),
+                    ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes=ws_bytes))
+            slots.append(slot)
+        streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        assert all(n % 4 == 0 for n in n_per)
+
+        def step_host(i):
+            st = streams[i % 2]
+            for s in slots[i % 2]:
+                _lib.check(_lib.lib.amtfeat_process_host(
+                    s['m']._dev_plan.handle, s['h_in'].data_ptr(), s['in_off'], s['n_arr'], s['out_off'], B,
+                    s['h_out'].data_ptr(), s['h_in'].numel(), s['h_out'].numel(), s['d_in'].data_ptr(),
+                    s['d_out'].data_ptr(), s['ws'].data_ptr(), s['ws_bytes'], st.cuda_stream))
+
+        for i in range(max(2, min(args.warmup, 3))):
+            step_host(i)
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(torch.cuda.default_stream(dev))
+        for st in streams:
+            st.wait_stream(torch.cuda.default_stream(dev))
+        for i in range(args.steps):
+            step_host(i)
+        for st in streams:
+            torch.cuda.default_stream(dev).wait_stream(st)
+        g1.record(torch.cuda.default_stream(dev))
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        ems = torch.tensor([max(g0.elapsed_time(g1), 0.0)], device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        checksum = float(slots[0][0]['h_out'][:1024].sum())  # the host really holds the features
+        e2e = {
+            'value': world * args.steps * hours_per_step / (float(ems.item()) / 1e3), 'unit': 'audio-hours/s',
+            'h2d_bytes_per_step': int(sum(4 * B * n for n in n_per)),
+            'd2h_bytes_per_step': int(sum(4 * s['h_out'].numel() for s in slots[0])),
+            'ms_per_step': float(ems.item()) / args.steps, 'wall_ms_per_step_rank0': wall_ms / args.steps,
+            'path': 'amtfeat_process_host (C-ABI): pinned host audio -> H2D -> kernels -> D2H of the full float32 features, '
+                    '2 pipeline slots', 'checksum': checksum,
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel + CPU baseline ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    kern = {}
+    for (mname, k), v in prof.items():
+        m = mods[[x.features_name() for x in mods].index(mname)]
+        n = n_per[mods.index(m)]
+        per_launch_ms = v['ms'] / max(v['launches'], 1)
+        bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n)
+        if k == 'decimate_kernel':  # one launch per ladder level: average over the levels
+            bytes_per_launch = bytes_per_launch / max(1, m.describe()['n_levels'] - 1)
+        kern[mname + '.' + k] = {'ms_total': v['ms'], 'launches': v['launches'], 'avg_ms': per_launch_ms,
+                                 'share_of_step': v['ms'] / ms_total,
+                                 'algorithmic_GBps': bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
+    top = max(kern.items(), key=lambda kv: kv[1]['ms_total'])
+    roofline = {'kernel': top[0], 'bound': 'hbm', 'achieved': top[1]['algorithmic_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': (top[1]['algorithmic_GBps'] or 0.0) / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'note': 'FP32-SIMT/shared-memory bound kernel (SURVEY.md 8d): the HBM fraction is reported as required; '
+                        'see DESIGN.md for the FP32 roofline', 'kernels': kern}
+    step_bytes = sum(B * algorithmic_bytes(m, n) for m, n in zip(mods, n_per))
+    roofline['step_algorithmic_GBps'] = step_bytes / (ms_total / args.steps * 1e-3) / 1e9
+
+    cpu = None
+    if not args.no_cpu:
+        sec = cpu_sample_seconds(args.workload)
+        t = _oracle_worker((args.workload, sec, 77))
+        cpu = {'value': sec / 3600.0 / t, 'unit': 'audio-hours/s', 'cores': 1, 'kind': 'port',
+               'sample': 'one %.0f s clip through the oracle float32 port of the same modules (%.1f s of CPU)' % (sec, t)}
+
+    launches = sum(int(_lib.lib.amtfeat_launch_count(m._dev_plan.handle, B, _lib.i64_array([n] * B)))
+                   for m, n in zip(mods, n_per))
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'audio-hours/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload + ': ' + desc, 'tracks_per_gpu_per_step': B, 'track_seconds': seconds,
+                   'audio_hours_per_step': world * hours_per_step,
+                   'l2': 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) exceeds the 126 MB L2'
+                         % (sum(4 * B * n for n in n_per) / 1e6, (step_bytes - sum(4 * B * n for n in n_per)) / 1e6),
+                   'parallelism': 'track-sharded x%d, no collective on the data path' % world},
+        'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c5', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='tracks per GPU per step (0 = workload default)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

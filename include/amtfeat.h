@@ -140,6 +140,15 @@ AMTFEAT_API int amtfeat_process_host(const amtfeat_plan *plan, const float *h_au
 /* Number of kernel launches amtfeat_process enqueues for this batch (bench.py's gpu_launches). */
 AMTFEAT_API int amtfeat_launch_count(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
 
+/*
+ * Measurement hook (no reference counterpart): when enabled, amtfeat_process records a CUDA event pair
+ * around every kernel it launches on the launching stream; amtfeat_profile_read waits for them and
+ * writes {"<kernel>": {"ms": total, "launches": n}, ...} as JSON, then clears the records.
+ * Single-threaded use only.
+ */
+AMTFEAT_API int amtfeat_profile_enable(amtfeat_plan *plan, int enable);
+AMTFEAT_API int amtfeat_profile_read(amtfeat_plan *plan, char *buf, size_t capacity);
+
 #ifdef __cplusplus
 }
 #endif
