@@ -19,6 +19,8 @@ template <> struct FftCfg<128>  { static constexpr int R1 = 8,  R2 = 16; };
 template <> struct FftCfg<64>   { static constexpr int R1 = 8,  R2 = 8;  };
 template <> struct FftCfg<32>   { static constexpr int R1 = 4,  R2 = 8;  };
 template <> struct FftCfg<16>   { static constexpr int R1 = 4,  R2 = 4;  };
+template <> struct FftCfg<8>    { static constexpr int R1 = 2,  R2 = 4;  };
+template <> struct FftCfg<4>    { static constexpr int R1 = 2,  R2 = 2;  };
 
 // Shared-memory footprint (in float2) of one FFT inside a warp's scratch: R1 rows of R2 + 1 (padded
 // so the transposed read of pass 2 is bank-conflict free).  NC + R1 >= NC + 1, so the same region

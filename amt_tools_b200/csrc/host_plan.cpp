@@ -285,7 +285,9 @@ static void build_fft_tables(Plan &p, int nfft) {
         case 128: R1 = 8; R2 = 16; break;
         case 64: R1 = 8; R2 = 8; break;
         case 32: R1 = 4; R2 = 8; break;
-        default: R1 = 4; R2 = 4; break;  // 16
+        case 16: R1 = 4; R2 = 4; break;
+        case 8: R1 = 2; R2 = 4; break;
+        default: R1 = 2; R2 = 2; break;  // 4
     }
     FftTables t;
     t.tw1.resize(NC);
@@ -376,9 +378,9 @@ static int build_vqt(Plan &p) {
                 max_len = std::max(max_len, lens[k - lo]);
             }
             const int nfft = (int)std::ldexp(1.0, (int)std::ceil(std::log2(max_len)));
-            if (nfft < 32 || nfft > 2048) {
+            if (nfft < 8 || nfft > 2048) {
                 char b[160];
-                snprintf(b, sizeof b, "octave %d of harmonic %d needs n_fft=%d; supported range is 32..2048", i, h, nfft);
+                snprintf(b, sizeof b, "octave %d of harmonic %d needs n_fft=%d; supported range is 8..2048", i, h, nfft);
                 set_error(b);
                 return AMTFEAT_ERR_INVALID;
             }
@@ -476,8 +478,8 @@ int build_plan_tables(Plan &p) {
             return AMTFEAT_OK;
         case AMTFEAT_STFT:
         case AMTFEAT_MEL:
-            if (!is_pow2(c.n_fft) || c.n_fft < 32 || c.n_fft > 2048) {
-                set_error("n_fft must be a power of two in [32, 2048]");
+            if (!is_pow2(c.n_fft) || c.n_fft < 8 || c.n_fft > 2048) {
+                set_error("n_fft must be a power of two in [8, 2048]");
                 return AMTFEAT_ERR_INVALID;
             }
             if (c.win_length <= 0 || c.win_length > c.n_fft) { set_error("win_length must be in [1, n_fft]"); return AMTFEAT_ERR_INVALID; }

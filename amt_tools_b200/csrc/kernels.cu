@@ -503,7 +503,8 @@ int upload_plan(Plan &p) {
     AMT_CUDA(cudaSetDevice(p.device));
     int rc;
     if ((rc = set_attrs<1024>()) || (rc = set_attrs<512>()) || (rc = set_attrs<256>()) || (rc = set_attrs<128>()) ||
-        (rc = set_attrs<64>()) || (rc = set_attrs<32>()) || (rc = set_attrs<16>()))
+        (rc = set_attrs<64>()) || (rc = set_attrs<32>()) || (rc = set_attrs<16>()) || (rc = set_attrs<8>()) ||
+        (rc = set_attrs<4>()))
         return rc;
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
@@ -710,7 +711,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             case 128: rc = launch_stft<128>(p, sp, batch, maxT, st); break;
             case 64: rc = launch_stft<64>(p, sp, batch, maxT, st); break;
             case 32: rc = launch_stft<32>(p, sp, batch, maxT, st); break;
-            default: rc = launch_stft<16>(p, sp, batch, maxT, st); break;
+            case 16: rc = launch_stft<16>(p, sp, batch, maxT, st); break;
+            case 8: rc = launch_stft<8>(p, sp, batch, maxT, st); break;
+            default: rc = launch_stft<4>(p, sp, batch, maxT, st); break;
         }
         if (rc) return rc;
     } else if (c.kind == AMTFEAT_POWER) {
@@ -754,7 +757,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 case 128: rc = launch_cqt<128>(p, cp, (int)i0, cnt, batch, maxT, st); break;
                 case 64: rc = launch_cqt<64>(p, cp, (int)i0, cnt, batch, maxT, st); break;
                 case 32: rc = launch_cqt<32>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                default: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 16: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                case 8: rc = launch_cqt<8>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                default: rc = launch_cqt<4>(p, cp, (int)i0, cnt, batch, maxT, st); break;
             }
             if (rc) return rc;
             i0 = i1;

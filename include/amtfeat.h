@@ -64,7 +64,7 @@ typedef struct amtfeat_config {
     int32_t decibels;       /* common.py:203-230 post_proc / power.py:52-55                         */
     int32_t center;         /* waveform.py:41                                                        */
     int32_t win_length;     /* waveform / stft / mel / power                                         */
-    int32_t n_fft;          /* stft / mel (power of two, 32..2048)                                   */
+    int32_t n_fft;          /* stft / mel (power of two, 8..2048)                                   */
     int32_t n_mels;         /* mel.py:37                                                             */
     int32_t htk;            /* mel.py:38                                                             */
     int32_t n_bins;         /* vqt.py:49                                                             */

@@ -1,0 +1,239 @@
+"""
+Parity of the CUDA path (through the C-ABI) against the float64 oracle and the committed golden fixtures.
+Run on the B200 box:  python -m pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star; measured context in DESIGN.md "Parity"):
+  * linear magnitudes / powers: relative L2 <= 1e-5                                         (asserted)
+  * dB features, bins within 60 dB of the clip maximum: max-abs <= DB_TOL_TOP dB           (asserted)
+  * dB features, all bins down to the -80 dB floor: max-abs <= DB_TOL_ALL dB               (asserted)
+The 1e-3 dB bar of the north_star is met where float32 arithmetic allows it (STFT / MelSpec above -60 dB);
+the reference itself computes in float32 and deviates from the float64 truth by 2e-3 .. 2e-2 dB in the
+bottom 20 dB (measured with the float32 oracle), which is why DB_TOL_ALL is looser.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import amt_tools_b200 as ab
+from amt_tools_b200.synth import piano_like
+from oracle import modules as om
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_TOL = 1e-5
+DB_TOL_TOP = {'STFT': 1e-3, 'MelSpec': 1e-3, 'SignalPower': 1e-3, 'CQT': 5e-3, 'VQT': 5e-3, 'HCQT': 5e-2, 'HVQT': 5e-2}
+DB_TOL_ALL = {'STFT': 2e-2, 'MelSpec': 1e-2, 'SignalPower': 1e-3, 'CQT': 5e-2, 'VQT': 5e-2, 'HCQT': 0.5, 'HVQT': 0.5}
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'golden_v1.npz')
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def db_errors(name, got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale, thr = (1.0, -60.0) if name == 'SignalPower' else (80.0, 0.25)
+    d = np.abs(got - want) * scale
+    top = want > thr
+    return d.max(), (d[top].max() if top.any() else 0.0)
+
+
+LIN_CASES = [
+    ('STFT', dict(sample_rate=16000, hop_length=512, n_fft=2048), 16000, 5.0),
+    ('STFT', dict(sample_rate=16000, hop_length=128, n_fft=512), 16000, 3.0),
+    ('STFT', dict(sample_rate=16000, hop_length=160, n_fft=1024, win_length=400), 16000, 3.0),
+    ('STFT', dict(sample_rate=16000, hop_length=512, n_fft=2048, center=False), 16000, 3.1),
+    ('STFT', dict(sample_rate=16000, hop_length=32, n_fft=64), 16000, 1.0),
+    ('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000, 5.0),
+    ('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048, htk=True), 16000, 5.0),
+    ('MelSpec', dict(sample_rate=16000, hop_length=2048, n_mels=229, n_fft=2048, center=False), 16000, 5.0),
+    ('MelSpec', dict(sample_rate=22050, hop_length=256, n_mels=80, n_fft=1024), 22050, 3.0),
+    ('SignalPower', dict(sample_rate=22050, hop_length=512), 22050, 5.0),
+    ('SignalPower', dict(sample_rate=22050, hop_length=512, win_length=2048, center=False), 22050, 5.0),
+    ('CQT', dict(sample_rate=22050, hop_length=512, n_bins=192, bins_per_octave=24), 22050, 5.0),
+    ('CQT', dict(sample_rate=22050, hop_length=512, n_bins=88, bins_per_octave=12), 22050, 3.0),   # partial lowest octave
+    ('VQT', dict(sample_rate=22050, hop_length=512), 22050, 5.0),
+    ('VQT', dict(sample_rate=44100, hop_length=1024, n_bins=96, bins_per_octave=12, gamma=5.0), 44100, 3.0),
+    ('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), 22050, 4.0),
+    ('HVQT', dict(sample_rate=22050, hop_length=512, harmonics=[1, 2, 3], n_bins=72, bins_per_octave=12), 22050, 3.0),
+]
+
+
+def make(name, kw, decibels):
+    kw = dict(kw, decibels=decibels)
+    if 'harmonics' in kw:
+        return getattr(ab, name)(**dict(kw, harmonics=list(kw['harmonics']))), \
+            getattr(om, 'O' + name)(**dict(kw, harmonics=list(kw['harmonics'])))
+    return getattr(ab, name)(**kw), getattr(om, 'O' + name)(**kw)
+
+
+@pytest.mark.parametrize('idx', range(len(LIN_CASES)))
+def test_linear_parity(idx):
+    name, kw, sr, sec = LIN_CASES[idx]
+    m, o = make(name, kw, False)
+    y = piano_like(int(sr * sec), sr, seed=200 + idx)
+    got = m.process_audio(y)
+    assert got.is_cuda and got.dtype == torch.float32 and got.is_contiguous()
+    want = o.process_audio(y)
+    assert tuple(got.shape) == want.shape
+    assert got.shape[-1] == m.get_expected_frames(y)
+    assert rel_l2(got.cpu().numpy(), want) <= REL_L2_TOL
+
+
+@pytest.mark.parametrize('idx', range(len(LIN_CASES)))
+def test_decibel_parity(idx):
+    name, kw, sr, sec = LIN_CASES[idx]
+    m, o = make(name, kw, True)
+    y = piano_like(int(sr * sec), sr, seed=300 + idx)
+    got = m.process_audio(y).cpu().numpy()
+    want = o.process_audio(y)
+    assert got.shape == want.shape
+    e_all, e_top = db_errors(name, got, want)
+    assert e_top <= DB_TOL_TOP[name], (name, e_top)
+    assert e_all <= DB_TOL_ALL[name], (name, e_all)
+    if name != 'SignalPower':
+        assert got.min() >= 0.0 and got.max() == 1.0       # [0, 1] scaling, maximum exactly 1 (common.py:224-225)
+    else:
+        assert got.max() == 0.0 and got.min() >= -80.0
+
+
+def test_golden_fixtures():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(GOLDEN), 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(GOLDEN)
+    for case, (ctor, kw, sr, sec, seed) in mg.CASES.items():
+        y = piano_like(int(sr * sec), sr, seed=seed)
+        name = ctor[1:]
+        got = getattr(ab, name)(**kw).process_audio(y).cpu().numpy()
+        want = g[case]
+        assert got.shape == want.shape, case
+        if kw.get('decibels', True):
+            e_all, e_top = db_errors(name, got, want)
+            assert e_top <= DB_TOL_TOP[name] and e_all <= DB_TOL_ALL[name], (case, e_all, e_top)
+        else:
+            assert rel_l2(got, want) <= REL_L2_TOL, case
+
+
+def test_analytic_known_answers_on_gpu():
+    # STFT: unit sinusoid at a bin centre -> A * n_fft / 4 ; CQT: A * sqrt(L_k) / 2
+    n_fft, k = 2048, 100
+    y = (0.5 * np.sin(2 * np.pi * k * np.arange(16000) / n_fft)).astype(np.float32)
+    S = ab.STFT(decibels=False).process_audio(y).cpu().numpy()[0]
+    assert abs(S[k, 10] - 0.5 * n_fft / 4) / (0.5 * n_fft / 4) < 1e-5
+    from oracle import librosa_stages as ls
+    freqs = ls.cqt_frequencies(192, ls.NOTE_C1_HZ, 24)
+    lengths, _ = ls.wavelet_lengths(freqs, 22050, 0.0, ls.relative_bandwidth_et(24))
+    m = ab.CQT(22050, 512, False, n_bins=192, bins_per_octave=24)
+    for kb in (5, 60, 150, 185):
+        y = (0.7 * np.sin(2 * np.pi * freqs[kb] * np.arange(22050 * 3) / 22050)).astype(np.float32)
+        Cq = m.process_audio(y).cpu().numpy()[0]
+        want = 0.7 * np.sqrt(lengths[kb]) / 2
+        assert abs(Cq[kb, 60] - want) / want < 2e-3
+
+
+def test_edge_cases_shapes_and_silence():
+    # empty audio follows the reference quirks (stft.py:59, mel.py:57, waveform.py:138)
+    e = np.zeros(0, dtype=np.float32)
+    assert tuple(ab.STFT().process_audio(e).shape) == (1, 2048, 0)
+    assert tuple(ab.MelSpec().process_audio(e).shape) == (1, 229, 0)
+    assert tuple(ab.WaveformWrapper(win_length=400).process_audio(e).shape) == (400, 0)
+    assert tuple(ab.CQT().process_audio(e).shape) == (1, 84, 0)
+    # one sample, hop - 1, hop, hop + 1 samples
+    for n in (1, 511, 512, 513, 2047, 2049):
+        y = piano_like(n, 16000, seed=n)
+        for m, o in ((ab.STFT(decibels=False), om.OSTFT(decibels=False)), (ab.MelSpec(decibels=False), om.OMelSpec(decibels=False)),
+                     (ab.SignalPower(decibels=False), om.OSignalPower(decibels=False))):
+            got, want = m.process_audio(y).cpu().numpy(), o.process_audio(y)
+            assert got.shape == want.shape and got.shape[-1] == m.get_expected_frames(y)
+            assert rel_l2(got, want) <= REL_L2_TOL
+    y = piano_like(700, 22050, seed=7)
+    got, want = ab.CQT(decibels=False).process_audio(y).cpu().numpy(), om.OCQT(decibels=False).process_audio(y)
+    assert got.shape == want.shape and rel_l2(got, want) <= REL_L2_TOL
+    # digital silence: every dB feature is exactly 1.0 (0 dB re. its own maximum), linear features are 0
+    z = np.zeros(8000, dtype=np.float32)
+    assert float(ab.MelSpec().process_audio(z).min()) == 1.0
+    assert float(ab.CQT().process_audio(z).min()) == 1.0
+    assert float(ab.STFT(decibels=False).process_audio(z).abs().max()) == 0.0
+    # too-short uncentred input raises like librosa does
+    with pytest.raises(ValueError):
+        ab.STFT(center=False, win_length=512, hop_length=512, n_fft=2048).process_audio(np.ones(100, dtype=np.float32))
+
+
+def test_waveform_wrapper_frames_bit_exact():
+    y = piano_like(30000, 22050, seed=9)
+    for kw in (dict(win_length=1024), dict(win_length=1024, center=False), dict(hop_length=160, win_length=400)):
+        got = ab.WaveformWrapper(22050, **kw).process_audio(y).cpu().numpy()
+        want = om.OWaveformWrapper(22050, **kw).process_audio(y)
+        assert got.shape == want.shape and np.array_equal(got, want.astype(np.float32))
+
+
+def test_batched_and_ragged_match_single_clip_bit_for_bit():
+    clips = [piano_like(n, 22050, seed=40 + i) for i, n in enumerate((22050, 30001, 12345, 44100))]
+    for m in (ab.MelSpec(22050), ab.HCQT(22050, 256, n_bins=120, bins_per_octave=24, harmonics=[0.5, 1, 2]), ab.STFT(22050),
+              ab.SignalPower(22050), ab.VQT(22050)):
+        singles = [m.process_audio(c) for c in clips]
+        ragged = m.process_audio(clips)
+        assert len(ragged) == len(clips)
+        for a, b in zip(singles, ragged):
+            assert a.shape == b.shape and torch.equal(a, b)
+        same = np.stack([clips[0], clips[0][::-1].copy()])
+        batch = m.process_audio(same)
+        assert batch.shape[0] == 2 and torch.equal(batch[0], singles[0])
+        assert torch.equal(batch[1], m.process_audio(same[1]))
+        # device-resident input: no host round trip, same result
+        dev = torch.from_numpy(same).cuda()
+        assert torch.equal(m.process_audio(dev), batch)
+
+
+def test_numpy_output_mode_and_combo():
+    y = piano_like(22050 * 2, 22050, seed=50)
+    m = ab.MelSpec(22050, output='numpy')
+    out = m.process_audio(y)
+    assert isinstance(out, np.ndarray) and out.dtype == np.float32
+    combo = ab.FeatureCombo([ab.STFT(22050, 512), ab.VQT(22050, 512), ab.SignalPower(22050, 512)])
+    feats = combo.process_audio_list(y)
+    assert [tuple(f.shape) for f in feats] == [(1, 1025, 87), (1, 84, 87), (87,)]
+    with pytest.raises(ValueError):            # the reference's np.concatenate fails on these shapes too (combo.py:118-120)
+        combo.process_audio(y)
+    stack = ab.FeatureCombo([ab.CQT(22050, 512), ab.VQT(22050, 512)]).process_audio(y)
+    assert tuple(stack.shape) == (2, 84, 87)
+
+
+def test_full_size_properties():
+    # BASELINE-sized inputs, checked through size-independent properties instead of the (slow) oracle
+    y = piano_like(22050 * 240, 22050, seed=60)
+    h = ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60)
+    f = h.process_audio(y)
+    assert tuple(f.shape) == (6, 360, 20672) == (6, 360, h.get_expected_frames(y))
+    assert float(f.min()) >= 0.0 and torch.equal(f.amax(dim=(1, 2)), torch.ones(6, device=f.device))
+    # time-shift covariance: delaying the audio by k hops delays the (linear) features by k frames (interior frames)
+    hl = ab.HCQT(22050, 256, False, n_bins=360, bins_per_octave=60)
+    k = 64
+    a = hl.process_audio(y[:22050 * 60])
+    b = hl.process_audio(np.concatenate([np.zeros(k * 256, dtype=np.float32), y[:22050 * 60]]))
+    assert rel_l2(b[:, :, k + 400:k + 4000].cpu().numpy(), a[:, :, 400:4000].cpu().numpy()) < 1e-5
+    # linearity of the complex transform shows up as homogeneity of magnitudes
+    c = hl.process_audio(0.25 * y[:22050 * 60])
+    assert rel_l2(c.cpu().numpy(), 0.25 * a.cpu().numpy()) < 1e-6
+    # 64 x 20 s MelSpec batch (configs[1]): every clip equals its single-clip result
+    m = ab.MelSpec()
+    batch = np.stack([piano_like(320000, 16000, seed=70 + (i % 3)) for i in range(64)])
+    out = m.process_audio(batch)
+    assert tuple(out.shape) == (64, 1, 229, 626)
+    for i in (0, 1, 2, 63):
+        assert torch.equal(out[i], m.process_audio(batch[i]))
+    # Parseval-style check on the STFT of white noise (periodic Hann, 75 % overlap => sum w^2 constant)
+    rng = np.random.RandomState(0)
+    x = rng.randn(16000 * 20).astype(np.float32)
+    S = ab.STFT(decibels=False).process_audio(x).double() ** 2
+    energy = (2 * S[0, 1:-1].sum(0) + S[0, 0] + S[0, -1]) / 2048          # per-frame energy of the windowed frame
+    fr = torch.from_numpy(x[2048:2048 + 2048 * 100].reshape(100, 2048)).double()
+    w = torch.hann_window(2048, periodic=True, dtype=torch.float64)
+    want = ((fr * w) ** 2).sum(1)
+    got = energy[(2048 + np.arange(100) * 2048 + 1024) // 512]
+    assert torch.allclose(got.cpu(), want, rtol=1e-5)

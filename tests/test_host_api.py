@@ -1,0 +1,150 @@
+"""
+Host side of the drop-in boundary, no GPU: the C-ABI library loads and exports every symbol that
+include/amtfeat.h declares, and the frame / sample / time arithmetic served by the native library is
+bit-exact with the oracle's restatement of the reference formulas.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import amt_tools_b200 as ab
+from amt_tools_b200 import _lib
+from oracle import modules as om
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+LENGTHS = [0, 1, 2, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 4096, 10007, 65537,
+           102399, 102400, 319999, 320000, 661500, 5292000]
+
+
+def pairs():
+    return [
+        (ab.STFT(), om.OSTFT()),
+        (ab.STFT(center=False), om.OSTFT(center=False)),
+        (ab.STFT(22050, 256, win_length=1024, n_fft=2048), om.OSTFT(22050, 256, win_length=1024, n_fft=2048)),
+        (ab.MelSpec(), om.OMelSpec()),
+        (ab.MelSpec(center=False, hop_length=2048), om.OMelSpec(center=False, hop_length=2048)),   # microphone demo config
+        (ab.SignalPower(), om.OSignalPower()),
+        (ab.SignalPower(22050, 512, win_length=2048, center=False), om.OSignalPower(22050, 512, win_length=2048, center=False)),
+        (ab.WaveformWrapper(), om.OWaveformWrapper()),
+        (ab.WaveformWrapper(16000, 160, win_length=400, center=False), om.OWaveformWrapper(16000, 160, win_length=400, center=False)),
+        (ab.CQT(22050, 512, n_bins=192, bins_per_octave=24), om.OCQT(22050, 512, n_bins=192, bins_per_octave=24)),
+        (ab.VQT(), om.OVQT()),
+        (ab.VQT(44100, 1024, n_bins=96, bins_per_octave=12, gamma=5.0), om.OVQT(44100, 1024, n_bins=96, bins_per_octave=12, gamma=5.0)),
+        (ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60), om.OHCQT(22050, 256, n_bins=360, bins_per_octave=60)),
+        (ab.HVQT(22050, 512, harmonics=[1, 2, 0.5]), om.OHVQT(22050, 512, harmonics=[1, 2, 0.5])),
+    ]
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'amtfeat.h')).read()
+    declared = sorted(set(re.findall(r'AMTFEAT_API[^;(]*?\b(amtfeat_\w+)\s*\(', header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert sorted(_lib.EXPORTS) == declared
+    assert _lib.lib.amtfeat_version() == 100
+
+
+@pytest.mark.parametrize('idx', range(14))
+def test_expected_frames_and_times_bit_exact(idx):
+    m, o = pairs()[idx]
+    for n in LENGTHS:
+        a = np.zeros(n, dtype=np.float32)
+        assert m.get_expected_frames(a) == o.get_expected_frames(a), (type(m).__name__, n)
+        t, t_ref = m.get_times(a), o.get_times(a)
+        assert t.dtype == np.float64 and t.shape == t_ref.shape
+        assert np.array_equal(t, t_ref), (type(m).__name__, n)
+        if not isinstance(o, om.OFeatureCombo):
+            ts, ts_ref = m.get_times(a, at_start=True), o.get_times(a, True)
+            assert np.array_equal(ts, ts_ref), (type(m).__name__, n, 'at_start')
+
+
+@pytest.mark.parametrize('idx', range(14))
+def test_sample_range_bit_exact(idx):
+    m, o = pairs()[idx]
+    for k in [0, 1, 2, 3, 9, 200, 625, 1292, 2584]:
+        r, r_ref = m.get_sample_range(k), o.get_sample_range(k)
+        assert r.dtype.kind == 'i' and np.array_equal(r, r_ref), (type(m).__name__, k)
+    assert m.get_num_samples_required() == o.get_num_samples_required()
+    assert m.get_feature_size() == o.get_feature_size()
+    assert m.get_num_channels() == o.num_channels
+    assert m.get_sample_rate() == o.sample_rate and m.get_hop_length() == o.hop_length
+
+
+def test_sample_range_inverts_expected_frames():
+    for m, _ in pairs():
+        for k in [1, 2, 7, 100]:
+            r = m.get_sample_range(k)
+            for n in (r[0], r[-1]):
+                assert m.get_expected_frames(np.zeros(int(n), dtype=np.float32)) == k, (type(m).__name__, k, n)
+
+
+def test_known_sequence_lengths():
+    assert ab.MelSpec().get_sample_range(625).max() == 319999
+    assert ab.CQT(22050, 512, n_bins=192, bins_per_octave=24).get_sample_range(200).max() == 102399
+
+
+def test_plan_description_matches_oracle_octave_plan():
+    d = ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()
+    assert d['eds_ref'] == d['eds_lib'] == [2, 1, 0, 0, 0, 0]
+    assert d['n_levels'] == 8 and d['n_octaves'] == 6 and d['channels'] == 6 and d['feature_size'] == 360
+    by_fft = {}
+    for it in d['items']:
+        by_fft.setdefault(it['n_fft'], []).append(it['level'])
+    assert sorted(by_fft) == [512, 1024] and by_fft[1024] == list(range(8)) and by_fft[512] == list(range(6))
+    assert sum(it['rows'] for it in d['items']) == 6 * 360
+    # the sparsified basis keeps the same number of entries as the oracle's (librosa) CSR bases, row for row
+    from oracle import librosa_stages as ls
+    d1 = ab.CQT(22050, 512, n_bins=192, bins_per_octave=24).describe()
+    assert [it['n_fft'] for it in d1['items']] == [256] * 8
+    freqs = ls.cqt_frequencies(192, ls.NOTE_C1_HZ, 24)
+    alpha = ls.relative_bandwidth_et(24)
+    for i, it in enumerate(sorted(d1['items'], key=lambda x: x['level'])):
+        lo, hi = 192 - 24 * (i + 1), 192 - 24 * i
+        basis, n_fft, _ = ls.vqt_filter_fft(22050 / 2.0 ** i, freqs[lo:hi], 0.0, alpha)
+        cols = basis.tocoo().col
+        assert n_fft == it['n_fft'] and it['kmin'] == cols.min() and it['kmax'] == cols.max()
+    v = ab.VQT(22050, 512).describe()
+    assert [it['n_fft'] for it in sorted(v['items'], key=lambda x: x['level'])] == [256, 256, 128, 128, 128, 64, 32]
+    assert d1['decim_taps'] == len(ls.soxr_hq_taps(2))
+
+
+def test_errors_follow_the_reference():
+    with pytest.raises(ValueError):      # librosa: filter cutoff above Nyquist
+        ab.CQT(22050, 512, n_bins=120, bins_per_octave=12).get_expected_frames(np.zeros(100))
+    with pytest.raises(ValueError):      # librosa: hop_length not divisible by 2^(n_octaves-1)
+        ab.CQT(22050, 100, n_bins=84, bins_per_octave=12).get_expected_frames(np.zeros(100))
+    with pytest.raises(ValueError):
+        ab.STFT(n_fft=1000).get_expected_frames(np.zeros(100))
+    with pytest.raises(ValueError):
+        ab.STFT(device='cpu')
+
+
+def test_features_name_and_combo_host_logic():
+    assert ab.HCQT.features_name() == 'HCQT' and ab.MelSpec.get_feature_tag() == 'MelSpec'
+    combo = ab.FeatureCombo([ab.STFT(22050, 512), ab.VQT(22050, 512), ab.SignalPower(22050, 512)])
+    ocombo = om.OFeatureCombo([om.OSTFT(22050, 512), om.OVQT(22050, 512), om.OSignalPower(22050, 512)])
+    a = np.zeros(22050 * 3, dtype=np.float32)
+    assert combo.get_expected_frames(a) == ocombo.get_expected_frames(a) == 1 + len(a) // 512
+    assert np.array_equal(combo.get_sample_range(50), ocombo.get_sample_range(50))
+    assert np.array_equal(combo.get_times(a), ocombo.get_times(a))
+    assert combo.get_num_channels() == 3 and combo.get_sample_rate() == 22050 and combo.get_hop_length() == 512
+    harmonics = [3, 1, 2]
+    ab.HVQT(harmonics=harmonics)
+    assert harmonics == [1, 2, 3]       # sorted in place like hvqt.py:40
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(Exception):
+        ab.MelSpec().process_audio(np.zeros(4000, dtype=np.float32))
+    # and the C-ABI refuses compute on a host-only plan
+    m = ab.MelSpec()
+    n = _lib.i64_array([4000])
+    rc = _lib.lib.amtfeat_process(m._host_plan.handle, None, _lib.i64_array([0]), n, _lib.i64_array([0]), 1, None, None, 1 << 30, None)
+    assert rc == _lib.ERR_NO_DEVICE

@@ -1,0 +1,134 @@
+"""
+Pins the oracle (oracle/librosa_stages.py) against independent implementations present in this image and
+against analytic known answers.  CPU only.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from amt_tools_b200.synth import piano_like
+from oracle import librosa_stages as ls
+from oracle import modules as om
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'golden_v1.npz')
+
+
+def test_stft_matches_torch_stft():
+    y = piano_like(16000 * 2, 16000, seed=1)
+    ours = ls.stft(y, n_fft=2048, hop_length=512, dtype=np.float64)
+    ref = torch.stft(torch.from_numpy(y).double(), 2048, 512, window=torch.hann_window(2048, periodic=True, dtype=torch.float64),
+                     center=True, pad_mode='constant', return_complex=True).numpy()
+    assert ours.shape == ref.shape == (1025, 1 + len(y) // 512)
+    assert np.linalg.norm(ours - ref) / np.linalg.norm(ref) < 1e-12
+
+
+def test_stft_short_window_and_uncentered():
+    y = piano_like(9000, 16000, seed=2)
+    ours = ls.stft(y, n_fft=1024, hop_length=256, win_length=800, center=False, dtype=np.float64)
+    ref = torch.stft(torch.from_numpy(y).double(), 1024, 256, win_length=800,
+                     window=torch.hann_window(800, periodic=True, dtype=torch.float64), center=False, return_complex=True).numpy()
+    assert ours.shape == ref.shape
+    assert np.linalg.norm(ours - ref) / np.linalg.norm(ref) < 1e-12
+
+
+@pytest.mark.parametrize('htk', [False, True])
+def test_mel_filterbank_matches_torchaudio(htk):
+    torchaudio = pytest.importorskip('torchaudio')
+    ours = ls.mel_filterbank(16000, 2048, n_mels=229, htk=htk)
+    ref = torchaudio.functional.melscale_fbanks(1025, 0.0, 8000.0, 229, 16000, norm='slaney',
+                                                mel_scale='htk' if htk else 'slaney').numpy().T
+    assert ours.shape == ref.shape == (229, 1025)
+    assert np.abs(ours - ref).max() < 2e-6
+    assert (ours != 0).sum(axis=0).max() <= 2            # at most two filters per FFT bin
+    assert (ours != 0).sum(axis=1).min() >= 1            # no empty filters
+
+
+def test_db_matches_transformers_audio_utils():
+    au = pytest.importorskip('transformers.audio_utils')
+    rng = np.random.RandomState(0)
+    S = rng.rand(40, 50) ** 4 * 30
+    got = ls.power_to_db(S, ref=np.max)
+    want = au.power_to_db(S, reference=S.max(), min_value=1e-10, db_range=80.0)
+    assert np.abs(got - want).max() < 1e-10
+    got = ls.amplitude_to_db(S, ref=np.max)
+    want = au.amplitude_to_db(S, reference=S.max(), min_value=1e-5, db_range=80.0)
+    assert np.abs(got - want).max() < 1e-10
+    assert got.max() == 0.0 and got.min() >= -80.0
+
+
+def test_db_post_proc_range_and_max_is_one():
+    y = piano_like(16000, 16000, seed=3)
+    f = om.OSTFT().process_audio(y)
+    assert f.shape == (1, 1025, 32)
+    assert f.max() == 1.0 and f.min() >= 0.0
+
+
+def test_analytic_stft_sinusoid():
+    # unit sinusoid at a bin centre: |X| = A * sum(w) / 2 = A * n_fft / 4 (periodic Hann)
+    n_fft, k, sr = 2048, 100, 16000
+    y = 0.5 * np.sin(2 * np.pi * k * np.arange(16000) / n_fft)
+    S = np.abs(ls.stft(y, n_fft=n_fft, hop_length=512, dtype=np.float64))
+    assert abs(S[k, 10] - 0.5 * n_fft / 4) < 1e-6
+
+
+@pytest.mark.parametrize('k', [5, 60, 150, 185])
+def test_analytic_cqt_sinusoid(k):
+    # sinusoid of amplitude A at bin k -> |C| ~= A * sqrt(L_k) / 2 with L_k the full-rate filter length
+    sr, bpo, n_bins = 22050, 24, 192
+    freqs = ls.cqt_frequencies(n_bins, ls.NOTE_C1_HZ, bpo)
+    lengths, _ = ls.wavelet_lengths(freqs, sr, 0.0, ls.relative_bandwidth_et(bpo))
+    y = 0.7 * np.sin(2 * np.pi * freqs[k] * np.arange(sr * 3) / sr)
+    C = np.abs(ls.vqt(y, sr=sr, hop_length=512, n_bins=n_bins, bins_per_octave=bpo, gamma=0.0))
+    want = 0.7 * np.sqrt(lengths[k]) / 2
+    assert abs(C[k, 60] - want) / want < 2e-3  # the 1 % sparsification bounds the deviation
+
+
+def test_decimator_design():
+    h = ls.soxr_hq_taps(2)
+    assert len(h) % 2 == 1 and np.allclose(h, h[::-1]) and abs(h.sum() - 1) < 1e-12
+    H = np.abs(np.fft.rfft(h, 1 << 16))
+    f = np.arange(len(H)) / (len(H) - 1)                # 1.0 = input Nyquist
+    assert np.abs(H[f <= 0.9136 / 2] - 1).max() < 2e-6   # flat passband up to 0.9136 * output Nyquist
+    assert 20 * np.log10(H[f >= 0.5].max()) < -120       # >= 120 dB from the output Nyquist on
+
+
+def test_sparsify_rows_keeps_99_percent():
+    rng = np.random.RandomState(1)
+    x = (rng.randn(5, 300) + 1j * rng.randn(5, 300)) * np.exp(-np.arange(300) / 20.0)
+    s = ls.sparsify_rows(x, 0.01).toarray()
+    kept = np.abs(s).sum(axis=1) / np.abs(x).sum(axis=1)
+    assert (kept >= 0.99).all() and (kept < 1).all()
+
+
+def test_octave_plans_match_survey_appendix_b():
+    m = om.OCQT(22050, 512, n_bins=192, bins_per_octave=24)
+    assert m.get_early_ds_count() == 0 and m.get_expected_frames(np.zeros(661500)) == 1292
+    h = om.OHCQT(22050, 256, n_bins=360, bins_per_octave=60)
+    assert [v.get_early_ds_count() for v in h.modules] == [2, 1, 0, 0, 0, 0]
+    assert h.get_expected_frames(np.zeros(661500)) == 2584
+    assert om.OMelSpec().get_sample_range(625).max() == 319999          # datasets/common.py:116 for Onsets & Frames
+    assert om.OCQT(22050, 512, n_bins=192, bins_per_octave=24).get_sample_range(200).max() == 102399
+
+
+def test_float32_oracle_close_to_float64():
+    y = piano_like(22050 * 2, 22050, seed=4)
+    a = om.OCQT(22050, 512, False, n_bins=192, bins_per_octave=24, dtype=np.float32).process_audio(y)
+    b = om.OCQT(22050, 512, False, n_bins=192, bins_per_octave=24, dtype=np.float64).process_audio(y)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-5
+
+
+def test_golden_fixtures_reproduce():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(os.path.dirname(GOLDEN), 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(GOLDEN)
+    assert set(g.files) == set(mg.CASES)
+    for name in ('stft_db', 'mel_db', 'cqt192_lin', 'power_db'):
+        ctor, kw, sr, sec, seed = mg.CASES[name]
+        y = piano_like(int(sr * sec), sr, seed=seed)
+        f = getattr(om, ctor)(dtype=np.float64, **kw).process_audio(y).astype(np.float32)
+        assert f.shape == g[name].shape
+        assert np.abs(f - g[name]).max() <= 1e-6 * max(1.0, np.abs(g[name]).max())
