@@ -149,7 +149,9 @@ __device__ __forceinline__ void rfft_split(float2 A, float2 B, float2 t, float2 
 }
 
 // 10 * log10(x) for x > 0 through the MUFU lg2 path (absolute error ~1e-6 dB, far below the 1e-3 dB bar).
-__device__ __forceinline__ float db10(float x) { return 3.0102999566398120f * __log2f(x); }
+// __fmul_rn keeps the product from being contracted into an FMA by a caller (the epilogue's `x - ref` must be exactly 0
+// at the maximum, common.py:224-225).
+__device__ __forceinline__ float db10(float x) { return __fmul_rn(3.0102999566398120f, __log2f(x)); }
 
 __device__ __forceinline__ void atomic_max_nonneg(float *addr, float v) {
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));  // valid ordering for non-negative floats

@@ -224,6 +224,24 @@ static void build_mel(Plan &p) {
             p.mel_w.insert(p.mel_w.end(), row.begin() + first, row.begin() + last + 1);
         }
     }
+    // padded, lane-major copy: filters m = 32 g + lane run in lockstep for steps[g] = max count in the group
+    const int ngroups = (n_mels + 31) / 32;
+    p.mel_gsteps.assign(ngroups, 0);
+    p.mel_goff.assign(ngroups, 0);
+    p.mel_wp.clear();
+    for (int gidx = 0; gidx < ngroups; ++gidx) {
+        int steps = 0;
+        for (int l = 0; l < 32 && 32 * gidx + l < n_mels; ++l) steps = std::max(steps, p.mel_cnt[32 * gidx + l]);
+        steps = (steps + 1) / 2 * 2;  // the kernel unrolls by two
+        p.mel_gsteps[gidx] = steps;
+        p.mel_goff[gidx] = (int32_t)p.mel_wp.size();
+        p.mel_wp.resize(p.mel_wp.size() + (size_t)steps * 32, 0.f);
+        for (int l = 0; l < 32 && 32 * gidx + l < n_mels; ++l) {
+            const int m = 32 * gidx + l;
+            for (int j = 0; j < p.mel_cnt[m]; ++j)
+                p.mel_wp[(size_t)p.mel_goff[gidx] + (size_t)j * 32 + l] = p.mel_w[p.mel_off[m] + j];
+        }
+    }
 }
 
 static double bessel_i0(double x) {
@@ -446,20 +464,79 @@ static int build_vqt(Plan &p) {
     }
     p.rows.clear();
     p.items.clear();
+    p.item_kmax_true.clear();
+    p.blocks.clear();
+    p.cgroups.clear();
+    p.weights4.clear();
     for (auto &g : groups) {
         CqtItem it{};
         it.nfft = g.first.first;
         it.level = g.first.second;
         it.hop = c.hop_length >> it.level;
-        it.row0 = (int32_t)p.rows.size();
         it.nrows = (int32_t)g.second.size();
         it.kmin = INT32_MAX;
         it.kmax = 0;
-        for (const CqtRow &rw : g.second) {
-            it.kmin = std::min(it.kmin, rw.col0);
-            it.kmax = std::max(it.kmax, rw.col0 + rw.cnt - 1);
-            p.rows.push_back(rw);
+        const int NC = it.nfft / 2;
+        // pair adjacent rows of the same (harmonic, octave) run into blocks
+        std::vector<CqtBlock> blks;
+        std::vector<std::pair<const CqtRow *, const CqtRow *>> members;
+        const std::vector<CqtRow> &rs = g.second;
+        for (size_t i = 0; i < rs.size();) {
+            const CqtRow *a = &rs[i], *b = nullptr;
+            if (i + 1 < rs.size() && rs[i + 1].chan == a->chan && rs[i + 1].bin == a->bin + 1) b = &rs[i + 1];
+            CqtBlock bl{};
+            bl.col0 = b ? std::min(a->col0, b->col0) : a->col0;
+            bl.chan_a = a->chan; bl.bin_a = a->bin; bl.inv_a = a->inv_len;
+            bl.chan_b = b ? b->chan : -1; bl.bin_b = b ? b->bin : 0; bl.inv_b = b ? b->inv_len : 0.f;
+            blks.push_back(bl);
+            members.push_back({a, b});
+            i += b ? 2 : 1;
         }
+        it.grp0 = (int32_t)p.cgroups.size();
+        for (size_t b0 = 0; b0 < blks.size(); b0 += 16) {
+            CqtGroup cg{};
+            cg.blk0 = (int32_t)(p.blocks.size());
+            cg.nblk = (int32_t)std::min<size_t>(16, blks.size() - b0);
+            int steps = 0;
+            for (int j = 0; j < cg.nblk; ++j) {
+                const auto &m = members[b0 + j];
+                int end = m.first->col0 + m.first->cnt;
+                if (m.second) end = std::max(end, m.second->col0 + m.second->cnt);
+                steps = std::max(steps, end - blks[b0 + j].col0);
+            }
+            cg.steps = steps;
+            cg.woff = (int32_t)p.weights4.size();
+            p.weights4.resize(p.weights4.size() + (size_t)steps * 16, cfloat4{0, 0, 0, 0});
+            for (int j = 0; j < cg.nblk; ++j) {
+                const auto &m = members[b0 + j];
+                const int col0 = blks[b0 + j].col0;
+                for (int s = 0; s < steps; ++s) {
+                    cfloat4 &w = p.weights4[(size_t)cg.woff + (size_t)s * 16 + j];
+                    const int col = col0 + s;
+                    if (col >= m.first->col0 && col < m.first->col0 + m.first->cnt) {
+                        const cfloat v = p.weights[m.first->woff + (col - m.first->col0)];
+                        w.ar = v.x; w.ai = v.y;
+                    }
+                    if (m.second && col >= m.second->col0 && col < m.second->col0 + m.second->cnt) {
+                        const cfloat v = p.weights[m.second->woff + (col - m.second->col0)];
+                        w.br = v.x; w.bi = v.y;
+                    }
+                }
+                it.kmin = std::min(it.kmin, col0);
+                it.kmax = std::max(it.kmax, std::min(NC, col0 + steps - 1));
+                p.blocks.push_back(blks[b0 + j]);
+            }
+            p.cgroups.push_back(cg);
+        }
+        it.ngrp = (int32_t)p.cgroups.size() - it.grp0;
+        int ktrue = 0;
+        it.row0 = (int32_t)p.rows.size();
+        for (const CqtRow &rw : rs) {
+            p.rows.push_back(rw);
+            ktrue = std::max(ktrue, rw.col0 + rw.cnt - 1);
+        }
+        p.item_kmax_true.push_back(ktrue);
+        it.kmax_true = ktrue;
         p.items.push_back(it);
     }
     return AMTFEAT_OK;
@@ -513,7 +590,7 @@ std::string describe(const Plan &p) {
     if (c.kind == AMTFEAT_MEL) o << ", \"mel_nnz\": " << p.mel_w.size();
     if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
         o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size()
-          << ", \"basis_nnz\": " << p.weights.size() << ", \"eds_ref\": [";
+          << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_steps\": " << p.weights4.size() / 16 * 16 << ", \"eds_ref\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_ref;
         o << "], \"eds_lib\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_lib;
@@ -521,7 +598,7 @@ std::string describe(const Plan &p) {
         for (size_t i = 0; i < p.items.size(); ++i) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
-              << ", \"rows\": " << it.nrows << ", \"kmin\": " << it.kmin << ", \"kmax\": " << it.kmax << "}";
+              << ", \"rows\": " << it.nrows << ", \"groups\": " << it.ngrp << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
         }
         o << "]";
     }

@@ -94,8 +94,8 @@ struct StftParams {
     float *maxbuf;
     const float *window;
     const float2 *tw1, *tw2;
-    const int *mel_start, *mel_cnt, *mel_off;
-    const float *mel_w;
+    const int *mel_start, *mel_gsteps, *mel_goff;
+    const float *mel_wp;
     int hop, pad, n_mels, decibels;
     int tile_floats;
 };
@@ -177,16 +177,25 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     float vmax = 0.f;
     float *out = p.out + cm->out_off;
     if (MODE == MODE_MEL) {
+        // sparse mel projection: filters 32 grp + lane advance in lockstep over the padded, lane-major weights
         const float *P = reinterpret_cast<const float *>(scr);
+        const int ngroups = (p.n_mels + 31) >> 5;
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
-            for (int m = lane; m < p.n_mels; m += 32) {
-                const int s = __ldg(p.mel_start + m), c = __ldg(p.mel_cnt + m);
-                const float *w = p.mel_w + __ldg(p.mel_off + m);
-                const float *pp = P + g * PP + s;
-                float acc = 0.f;
-                for (int j = 0; j < c; ++j) acc = fmaf(__ldg(w + j), pp[j], acc);
-                s_stage[m * (TT + 1) + warp * G + g] = acc;
+#pragma unroll 1
+            for (int grp = 0; grp < ngroups; ++grp) {
+                const int m = grp * 32 + lane;
+                const bool active = m < p.n_mels;
+                const int steps = __ldg(p.mel_gsteps + grp);
+                const float *w = p.mel_wp + __ldg(p.mel_goff + grp) + lane;
+                const float *pp = P + g * PP + (active ? __ldg(p.mel_start + m) : 0);
+                float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 2
+                for (int j = 0; j < steps; j += 2) {
+                    acc0 = fmaf(__ldg(w + j * 32), pp[j], acc0);
+                    acc1 = fmaf(__ldg(w + j * 32 + 32), pp[j + 1], acc1);
+                }
+                if (active) s_stage[m * (TT + 1) + warp * G + g] = acc0 + acc1;
             }
         }
         __syncthreads();
@@ -265,17 +274,34 @@ __global__ void __launch_bounds__(kThreads) frames_kernel(const float *__restric
 // K6 : dB epilogue (common.py:199 + 224-225, mel.py:94, power.py:55)
 // ------------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ float db_finish(float v, float ref_db, int scale01) {
+    v = fmaxf(v - ref_db, -80.0f);
+    return scale01 ? v / 80.0f + 1.0f : v;
+}
+
 __global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict__ out, const ClipMeta *__restrict__ meta,
                                                                 const float *__restrict__ maxbuf, int C, int F, int scale01) {
     const int seg = blockIdx.y, b = seg / C, c = seg % C;
-    const ClipMeta cm = meta[b];
-    const long long count = (long long)F * cm.T;
-    float *o = out + cm.out_off + (long long)c * count;
+    const ClipMeta *cm = meta + b;
+    const long long count = (long long)F * cm->T;
+    float *o = out + cm->out_off + (long long)c * count;
     const float ref_db = db10(fmaxf(1e-10f, maxbuf[seg]));
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < count; i += (long long)gridDim.x * kThreads) {
-        float v = fmaxf(o[i] - ref_db, -80.0f);
-        if (scale01) v = v / 80.0f + 1.0f;
-        o[i] = v;
+    // scalar head up to 16-byte alignment, float4 body, scalar tail
+    const long long head = min(count, (long long)(((16 - (reinterpret_cast<uintptr_t>(o) & 15)) & 15) >> 2));
+    const long long nvec = (count - head) >> 2;
+    const long long tail0 = head + (nvec << 2);
+    float4 *o4 = reinterpret_cast<float4 *>(o + head);
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
+        float4 v = o4[i];
+        v.x = db_finish(v.x, ref_db, scale01);
+        v.y = db_finish(v.y, ref_db, scale01);
+        v.z = db_finish(v.z, ref_db, scale01);
+        v.w = db_finish(v.w, ref_db, scale01);
+        o4[i] = v;
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < head) o[threadIdx.x] = db_finish(o[threadIdx.x], ref_db, scale01);
+        if (tail0 + threadIdx.x < count) o[tail0 + threadIdx.x] = db_finish(o[tail0 + threadIdx.x], ref_db, scale01);
     }
 }
 
@@ -285,8 +311,34 @@ __global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict
 // so every shared-memory access is unit stride.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kDecTile = 1024;  // outputs per CTA
-constexpr int kDecR = kDecTile / kThreads;
+constexpr int kDecR = 16;                       // consecutive outputs per thread (register sliding window)
+constexpr int kDecTile = kThreads * kDecR;      // outputs per CTA
+
+// Skewed shared-memory index: 4 extra floats per 32 so that 16-byte loads at a 64-byte lane stride are conflict free.
+__device__ __forceinline__ int dec_phys(int i) { return i + ((i >> 5) << 2); }
+
+__host__ __device__ inline int dec_front_pad(int D) { return ((((7 - D) % 4) + 4) % 4) + 8; }
+__host__ __device__ inline int dec_jtot(int D) { return (D + 1 + 7) / 8 * 8; }
+
+// One polyphase branch: acc[r] += sum_j h[j] * A[wbase - j + r], A skewed in shared memory.
+__device__ __forceinline__ void dec_branch(const float *__restrict__ A, const float *__restrict__ h, int jtot, int wbase,
+                                           float (&acc)[kDecR]) {
+#pragma unroll 1
+    for (int j0 = 0; j0 < jtot; j0 += 8) {
+        const float4 h0 = *reinterpret_cast<const float4 *>(h + j0), h1 = *reinterpret_cast<const float4 *>(h + j0 + 4);
+        const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        float v[24];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const float4 x = *reinterpret_cast<const float4 *>(A + dec_phys(wbase - 7 - j0 + 4 * q));
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+            for (int r = 0; r < kDecR; ++r) acc[r] = fmaf(hv[jj], v[7 - jj + r], acc[r]);
+    }
+}
 
 __global__ void __launch_bounds__(kThreads) decimate_kernel(const float *__restrict__ audio, float *__restrict__ ladder,
                                                              const ClipMeta *__restrict__ meta, const float *__restrict__ taps,
@@ -298,34 +350,48 @@ __global__ void __launch_bounds__(kThreads) decimate_kernel(const float *__restr
     if (m0 >= len_out) return;
     const float *src = (level_out == 1 ? audio : ladder) + cm->lvl_off[level_out - 1];
     float *dst = ladder + cm->lvl_off[level_out];
-    const int D = (ntaps - 1) / 2, ne = kDecTile + D, nhe = D + 1, nho = D;
-    float *xe = smem, *xo = xe + ne + 16, *he = xo + ne, *ho = he + nhe;
-    const long long base = 2ll * m0 - D;  // even
-    for (int i = threadIdx.x; i < 2 * ne; i += kThreads) {
-        const long long g = base + i;
-        const float v = (g >= 0 && g < len_in) ? __ldg(src + g) : 0.f;
-        ((i & 1) ? xo : xe)[i >> 1] = v;
+    const int D = (ntaps - 1) / 2;                 // even (host pads the taps), so `base` below is even
+    const int FP = dec_front_pad(D), jtot = dec_jtot(D);
+    const int len = FP + kDecTile + D + 8;         // logical length of each branch array
+    const int plen = (dec_phys(len) + 7) & ~3;
+    float *E = smem, *O2 = E + plen, *he = O2 + plen, *ho = he + jtot;
+    const long long base = 2ll * m0 - D;
+    // E[FP + e] = x[base + 2e],  O2[FP + e] = x[base + 2e - 1]   (e = 0 .. kDecTile + D - 1)
+    for (int e = threadIdx.x; e < kDecTile + D; e += kThreads) {
+        const long long g = base + 2ll * e;
+        float2 v;
+        if (g >= 0 && g + 1 < len_in) {
+            v = __ldg(reinterpret_cast<const float2 *>(src + g));
+        } else {
+            v.x = (g >= 0 && g < len_in) ? __ldg(src + g) : 0.f;
+            v.y = (g + 1 >= 0 && g + 1 < len_in) ? __ldg(src + g + 1) : 0.f;
+        }
+        E[dec_phys(FP + e)] = v.x;
+        O2[dec_phys(FP + e + 1)] = v.y;
     }
-    for (int i = threadIdx.x; i < ntaps; i += kThreads) ((i & 1) ? ho : he)[i >> 1] = __ldg(taps + i);
+    for (int i = threadIdx.x; i < FP; i += kThreads) { E[dec_phys(i)] = 0.f; O2[dec_phys(i)] = 0.f; }
+    if (threadIdx.x == 0) O2[dec_phys(FP)] = 0.f;
+    for (int i = threadIdx.x; i < 8; i += kThreads) { E[dec_phys(FP + kDecTile + D + i)] = 0.f; }
+    for (int j = threadIdx.x; j < jtot; j += kThreads) {
+        he[j] = (2 * j < ntaps) ? __ldg(taps + 2 * j) : 0.f;
+        ho[j] = (2 * j + 1 < ntaps) ? __ldg(taps + 2 * j + 1) : 0.f;
+    }
     __syncthreads();
     float acc[kDecR];
 #pragma unroll
     for (int r = 0; r < kDecR; ++r) acc[r] = 0.f;
-    const int mm = threadIdx.x;
-    for (int j = 0; j < nhe; ++j) {
-        const float h = he[j];
+    const int wbase = FP + kDecR * threadIdx.x + D;   // FP + D - 7 is a multiple of 4 by construction
+    dec_branch(E, he, jtot, wbase, acc);
+    dec_branch(O2, ho, jtot, wbase, acc);
+    const int m = m0 + kDecR * threadIdx.x;
+    if (m + kDecR <= len_out) {
 #pragma unroll
-        for (int r = 0; r < kDecR; ++r) acc[r] = fmaf(h, xe[mm + kThreads * r + D - j], acc[r]);
-    }
-    for (int j = 0; j < nho; ++j) {
-        const float h = ho[j];
+        for (int q = 0; q < kDecR / 4; ++q)
+            *reinterpret_cast<float4 *>(dst + m + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
 #pragma unroll
-        for (int r = 0; r < kDecR; ++r) acc[r] = fmaf(h, xo[mm + kThreads * r + D - j - 1], acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < kDecR; ++r) {
-        const int m = m0 + mm + kThreads * r;
-        if (m < len_out) dst[m] = acc[r];
+        for (int r = 0; r < kDecR; ++r)
+            if (m + r < len_out) dst[m + r] = acc[r];
     }
 }
 
@@ -339,40 +405,28 @@ struct CqtParams {
     const ClipMeta *meta;
     float *maxbuf;
     const CqtItem *items;
+    const CqtGroup *groups;
+    const CqtBlock *blocks;
+    const float4 *weights4;
     const CqtRow *rows;
     const float2 *weights;
     const float2 *tw1, *tw2;
-    int C, F, decibels, tile_floats, stage_rows;
+    int C, F, decibels, tile_floats, stage_groups, stage_rows;
 };
 
+// Shared prologue of both CQT kernels: stage the level signal, run the warp FFT unit.
 template <int NC>
-__global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
+__device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem &it, const ClipMeta *cm, int t0, float2 *s_tw1,
+                                              float2 *s_tw2, float *s_scr, float *s_tile) {
     using L = FftLayout<NC>;
-    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, NFFT = 2 * NC;
-    constexpr int WP2 = L::WARP_PITCH / 2;  // warp pitch in float2
-    extern __shared__ __align__(16) float smem[];
-    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
-    float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
-    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH
-    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // tile_floats
-    float *s_stage = s_tile + p.tile_floats;                          // stage_rows * (TT + 1)
-    __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
-
+    constexpr int G = L::G, TT = kWarpsPerCta * G, NFFT = 2 * NC, WP2 = L::WARP_PITCH / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const ClipMeta *cm = p.meta + blockIdx.y;
-    const int T = cm->T;
-    const int t0 = blockIdx.x * TT;
-    if (t0 >= T) return;
-    const CqtItem it = p.items[blockIdx.z];
-
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i <= NC; i += kThreads) s_tw2[i] = p.tw2[i];
-    if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
     const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
     int shift, fstride;
     load_tile(s_tile, src, cm->lvl_len[it.level], (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
     __syncthreads();
-
     float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
     const bool vec_ok = ((shift | fstride) & 1) == 0;
     if (vec_ok) {
@@ -385,9 +439,159 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
             return make_float2(x[0], x[1]);
         });
     }
+}
 
-    // real-FFT split restricted to the band [kmin, kmax] any row of this item touches -> D[g][k - kmin]
-    const int kb = it.kmax - it.kmin + 1;
+// Main kernel (n_fft >= 128).  Phase A: per-warp FFT + real-FFT split restricted to the band the item's rows touch,
+// D[t][k - kmin] left in the warps' scratch.  Phase B: every half-warp takes one group of 16 row blocks and one
+// chunk of 8 frames; a thread accumulates 2 rows x 8 frames in registers, so each weight fetch (one coalesced
+// 16-byte load) feeds 16 complex MACs and each D fetch feeds 2.
+template <int NC>
+__global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
+    using L = FftLayout<NC>;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2;
+    constexpr int NCH = TT / 8;  // chunks of 8 frames
+    extern __shared__ __align__(16) float smem[];
+    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
+    float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH
+    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // tile_floats
+    float *s_stage = s_tile + p.tile_floats;                          // stage_groups * 32 rows * (TT + 1)
+    int *s_rowoff = reinterpret_cast<int *>(s_stage + p.stage_groups * 32 * (TT + 1));  // stage_groups * 32
+    __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int T = cm->T;
+    const int t0 = blockIdx.x * TT;
+    if (t0 >= T) return;
+    const CqtItem it = p.items[blockIdx.z];
+    if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
+    cqt_fft_phase<NC>(p, it, cm, t0, s_tw1, s_tw2, s_scr, s_tile);
+
+    {   // real-FFT split on the band [kmin, kmax]
+        float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
+        const int kb = it.kmax - it.kmin + 1;
+        constexpr int JB = (NC + 1 + 31) / 32;
+        float2 X[G][JB];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                const int kk = lane + 32 * j;
+                if (kk < kb) {
+                    const int k = it.kmin + kk;
+                    const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
+                    float2 E, Tw;
+                    rfft_split(A, B, s_tw2[k], E, Tw);
+                    X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
+                }
+            }
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int j = 0; j < JB; ++j) {
+                const int kk = lane + 32 * j;
+                if (kk < kb) scr[g * S + kk] = X[g][j];
+            }
+    }
+    __syncthreads();
+
+    const float2 *D = reinterpret_cast<const float2 *>(s_scr);
+    float *out = p.out + cm->out_off;
+    const int l16 = tid & 15;
+    for (int g0 = 0; g0 < it.ngrp; g0 += p.stage_groups) {
+        const int ng = min(p.stage_groups, it.ngrp - g0);
+        // output row offsets of this pass (row slot = 2 * (16 * group + block) + {a, b})
+        for (int rs = tid; rs < ng * 32; rs += kThreads) {
+            const CqtGroup cg = p.groups[it.grp0 + g0 + (rs >> 5)];
+            const int l = (rs >> 1) & 15;
+            int off = -1;
+            if (l < cg.nblk) {
+                const CqtBlock *bl = p.blocks + cg.blk0 + l;
+                const int chan = (rs & 1) ? bl->chan_b : bl->chan_a, bin = (rs & 1) ? bl->bin_b : bl->bin_a;
+                if (chan >= 0) off = chan * p.F + bin;
+            }
+            s_rowoff[rs] = off;
+        }
+        for (int hw = tid >> 4; hw < ng * NCH; hw += kThreads / 16) {
+            const int gi = hw / NCH, ch = hw % NCH;
+            const CqtGroup cg = p.groups[it.grp0 + g0 + gi];
+            if (l16 < cg.nblk) {
+                const CqtBlock bl = p.blocks[cg.blk0 + l16];
+                const float4 *w = p.weights4 + cg.woff + l16;
+                // frame f of the chunk sits at foff(f) float2 from Dp
+#define AMT_FOFF(f) (G >= 8 ? (f) * S : ((f) / G) * WP2 + ((f) % G) * S)
+                const int tb = ch * 8;
+                const float2 *Dp = D + (tb / G) * WP2 + (G >= 8 ? (tb % G) * S : 0) + (bl.col0 - it.kmin);
+                float2 a[8], b[8];
+#pragma unroll
+                for (int f = 0; f < 8; ++f) a[f] = b[f] = make_float2(0.f, 0.f);
+#pragma unroll 2
+                for (int s = 0; s < cg.steps; ++s) {
+                    const float4 wv = __ldg(w + s * 16);
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) {
+                        const float2 d = Dp[AMT_FOFF(f) + s];
+                        a[f].x = fmaf(wv.x, d.x, a[f].x);
+                        a[f].x = fmaf(-wv.y, d.y, a[f].x);
+                        a[f].y = fmaf(wv.x, d.y, a[f].y);
+                        a[f].y = fmaf(wv.y, d.x, a[f].y);
+                        b[f].x = fmaf(wv.z, d.x, b[f].x);
+                        b[f].x = fmaf(-wv.w, d.y, b[f].x);
+                        b[f].y = fmaf(wv.z, d.y, b[f].y);
+                        b[f].y = fmaf(wv.w, d.x, b[f].y);
+                    }
+                }
+                float vmax = 0.f;
+                float *st = s_stage + (gi * 32 + 2 * l16) * (TT + 1) + tb;
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    const float pa = fmaf(a[f].x, a[f].x, a[f].y * a[f].y) * bl.inv_a;
+                    const float pb = fmaf(b[f].x, b[f].x, b[f].y * b[f].y) * bl.inv_b;
+                    if (t0 + tb + f < T) vmax = fmaxf(vmax, fmaxf(pa, pb));
+                    st[f] = p.decibels ? db10(fmaxf(1e-10f, pa)) : sqrtf(pa);
+                    st[(TT + 1) + f] = p.decibels ? db10(fmaxf(1e-10f, pb)) : sqrtf(pb);
+                }
+                if (p.decibels) atomicMax(&s_max[bl.chan_a], __float_as_int(vmax));
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < ng * 32 * TT; idx += kThreads) {
+            const int t = idx % TT, rs = idx / TT;
+            const int off = s_rowoff[rs];
+            if (off >= 0 && t0 + t < T) out[(long long)off * T + t0 + t] = s_stage[rs * (TT + 1) + t];
+        }
+        __syncthreads();
+    }
+    if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
+}
+
+// Fallback for tiny transforms (n_fft <= 64: the lowest octaves of a VQT with a large gamma): one thread per
+// (row, chunk of 8 frames) on the per-row tables.  Negligible share of any workload.
+template <int NC>
+__global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams p) {
+    using L = FftLayout<NC>;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2;
+    extern __shared__ __align__(16) float smem[];
+    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);
+    float2 *s_tw2 = s_tw1 + NC;
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);
+    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;
+    float *s_stage = s_tile + p.tile_floats;                          // stage_rows * (TT + 1)
+    __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int T = cm->T;
+    const int t0 = blockIdx.x * TT;
+    if (t0 >= T) return;
+    const CqtItem it = p.items[blockIdx.z];
+    if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
+    cqt_fft_phase<NC>(p, it, cm, t0, s_tw1, s_tw2, s_scr, s_tile);
+
+    float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
+    const int kb = it.kmax_true - it.kmin + 1;
     {
         constexpr int JMAX = (G * (NC + 1) + 31) / 32;
         float2 X[JMAX];
@@ -415,7 +619,6 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     }
     __syncthreads();
 
-    // sparse complex projection: one thread per (row, chunk of 8 frames)
     const float2 *D = reinterpret_cast<const float2 *>(s_scr);
     float *out = p.out + cm->out_off;
     for (int rc = 0; rc < it.nrows; rc += p.stage_rows) {
@@ -484,8 +687,13 @@ template <int NC> static size_t stft_smem(int tile_floats, int n_mels, bool mel)
 template <int NC> static size_t cqt_smem(int tile_floats, int stage_rows) {
     using L = FftLayout<NC>;
     size_t fl = 2 * NC + 2 * (NC + 2) + (size_t)kWarpsPerCta * L::WARP_PITCH + tile_floats +
-                (size_t)stage_rows * (kWarpsPerCta * L::G + 1);
+                (size_t)stage_rows * (kWarpsPerCta * L::G + 1) + stage_rows;
     return fl * sizeof(float);
+}
+template <int NC> static constexpr bool cqt_use_blocks() { return NC >= 64; }
+template <int NC> static cudaError_t cqt_set_attr() {
+    if (cqt_use_blocks<NC>()) return cudaFuncSetAttribute(cqt_kernel<(NC >= 64 ? NC : 64)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    return cudaFuncSetAttribute(cqt_small_kernel<(NC < 64 ? NC : 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 }
 static int tile_floats_for(int TT, int hop, int nfft) {
     int fl = hop <= nfft ? (TT - 1) * hop + nfft + 8 : TT * nfft;
@@ -495,7 +703,7 @@ static int tile_floats_for(int TT, int hop, int nfft) {
 template <int NC> static int set_attrs() {
     AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_STFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(stft_kernel<NC, MODE_MEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    AMT_CUDA(cudaFuncSetAttribute(cqt_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    AMT_CUDA(cqt_set_attr<NC>());
     return AMTFEAT_OK;
 }
 
@@ -515,6 +723,12 @@ int upload_plan(Plan &p) {
     if ((rc = upload_vec(p, p.taps, &p.d_taps))) return rc;
     if ((rc = upload_vec(p, p.rows, &p.d_rows))) return rc;
     if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
+    if ((rc = upload_vec(p, p.blocks, &p.d_blocks))) return rc;
+    if ((rc = upload_vec(p, p.cgroups, &p.d_cgroups))) return rc;
+    if ((rc = upload_vec(p, p.weights4, &p.d_weights4))) return rc;
+    if ((rc = upload_vec(p, p.mel_wp, &p.d_mel_wp))) return rc;
+    if ((rc = upload_vec(p, p.mel_gsteps, &p.d_mel_gsteps))) return rc;
+    if ((rc = upload_vec(p, p.mel_goff, &p.d_mel_goff))) return rc;
     if ((rc = upload_vec(p, p.items, &p.d_items))) return rc;
     for (auto &kv : p.fft) {
         if ((rc = upload_vec(p, kv.second.tw1, &kv.second.d_tw1))) return rc;
@@ -640,23 +854,34 @@ template <int NC>
 static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int batch, int maxT, cudaStream_t st) {
     using L = FftLayout<NC>;
     const int TT = kWarpsPerCta * L::G;
-    int maxhop = 0, maxrows = 0;
+    int maxhop = 0, maxrows = 0, maxgrp = 0;
     for (int i = item0; i < item0 + nitems; ++i) {
         maxhop = std::max(maxhop, p.items[i].hop);
         maxrows = std::max(maxrows, p.items[i].nrows);
+        maxgrp = std::max(maxgrp, p.items[i].ngrp);
     }
     cp.tile_floats = tile_floats_for(TT, maxhop, 2 * NC);
-    cp.stage_rows = std::max(1, std::min(maxrows, 3072 / (TT + 1)));
     cp.items = p.d_items + item0;
     const FftTables &ft = p.fft.at(NC);
     cp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1);
     cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
-    const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
-    if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
     dim3 grid((maxT + TT - 1) / TT, batch, nitems);
     static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
-    ProfScope ps(p, nm.c_str(), st);
-    cqt_kernel<NC><<<grid, kThreads, smem, st>>>(cp);
+    if (cqt_use_blocks<NC>()) {
+        cp.stage_groups = std::max(1, std::min(maxgrp, 4480 / (32 * (TT + 1))));
+        cp.stage_rows = cp.stage_groups * 32;
+        const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
+        if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+        ProfScope ps(p, nm.c_str(), st);
+        cqt_kernel<(NC >= 64 ? NC : 64)><<<grid, kThreads, smem, st>>>(cp);
+    } else {
+        cp.stage_groups = 0;
+        cp.stage_rows = std::max(1, std::min(maxrows, 3072 / (TT + 1)));
+        const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
+        if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+        ProfScope ps(p, nm.c_str(), st);
+        cqt_small_kernel<(NC < 64 ? NC : 32)><<<grid, kThreads, smem, st>>>(cp);
+    }
     AMT_CUDA(cudaGetLastError());
     return AMTFEAT_OK;
 }
@@ -701,7 +926,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         StftParams sp{};
         sp.audio = d_audio; sp.out = d_out; sp.meta = d_meta; sp.maxbuf = d_max; sp.window = p.d_window;
         sp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1); sp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
-        sp.mel_start = p.d_mel_start; sp.mel_cnt = p.d_mel_cnt; sp.mel_off = p.d_mel_off; sp.mel_w = p.d_mel_w;
+        sp.mel_start = p.d_mel_start; sp.mel_gsteps = p.d_mel_gsteps; sp.mel_goff = p.d_mel_goff; sp.mel_wp = p.d_mel_wp;
         sp.hop = c.hop_length; sp.pad = c.center ? c.n_fft / 2 : 0; sp.n_mels = c.n_mels; sp.decibels = c.decibels;
         sp.tile_floats = tile_floats_for(kWarpsPerCta * (1024 / NC), c.hop_length, c.n_fft);
         switch (NC) {
@@ -732,7 +957,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
     } else {
         // decimation ladder (levels 1 .. n_levels-1), then one launch per distinct n_fft
         const int ntaps = (int)p.taps.size(), D = (ntaps - 1) / 2;
-        const size_t dsmem = (size_t)(2 * (kDecTile + D) + 16 + ntaps + 8) * sizeof(float);
+        const int dlen = dec_front_pad(D) + kDecTile + D + 8;
+        const int dplen = ((dlen + ((dlen >> 5) << 2)) + 7) & ~3;
+        const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
@@ -744,6 +971,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         CqtParams cp{};
         cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
         cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
+        cp.groups = p.d_cgroups; cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
         cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
         size_t i0 = 0;
         while (i0 < p.items.size()) {

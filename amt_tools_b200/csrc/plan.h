@@ -40,9 +40,29 @@ struct CqtRow {
     int32_t woff;      // offset into the weight array
 };
 
+// Two adjacent rows of one (harmonic, octave) run, projected together so every FFT bin fetched from
+// shared memory feeds two complex MACs.  Row b is absent (chan_b < 0) for an odd-length run.
+struct CqtBlock {
+    int32_t col0;               // first FFT bin of the union band of both rows
+    int32_t chan_a, bin_a, chan_b, bin_b;
+    float inv_a, inv_b;         // 1 / length of each row (applied to the power)
+    int32_t pad_;
+};
+
+// 16 consecutive blocks: the unit of work of one half-warp.  Weights are stored [step][16 blocks] as
+// (re_a, im_a, re_b, im_b) so a half-warp's load of one step is one contiguous 256-byte line.
+struct CqtGroup {
+    int32_t blk0, nblk, steps, woff;
+};
+
 // All rows that consume the FFT frames of one (ladder level, n_fft) pair.
 struct CqtItem {
-    int32_t level, nfft, hop, row0, nrows, kmin, kmax, pad_;
+    int32_t level, nfft, hop, grp0, ngrp, kmin, kmax, nrows;
+    int32_t row0, kmax_true;    // per-row tables (small-n_fft fallback kernel); last bin with a non-zero weight
+};
+
+struct cfloat4 {
+    float ar, ai, br, bi;
 };
 
 // FFT constant tables for one complex length NC = n_fft / 2.
@@ -72,9 +92,15 @@ struct Plan {
     int n_oct = 0, n_filters = 0, n_levels = 0;
     std::vector<HarmonicInfo> harm;
     std::vector<float> taps;                   // 2:1 decimator, includes the sqrt(2) of `scale=True`
-    std::vector<CqtRow> rows;
-    std::vector<cfloat> weights;
+    std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
+    std::vector<cfloat> weights;               // per-row weights (host only)
+    std::vector<CqtBlock> blocks;
+    std::vector<CqtGroup> cgroups;
+    std::vector<cfloat4> weights4;
     std::vector<CqtItem> items;
+    std::vector<int32_t> item_kmax_true;       // last FFT bin with a non-zero weight, per item (describe / tests)
+    std::vector<float> mel_wp;                 // mel weights, padded [group of 32 filters][step][lane]
+    std::vector<int32_t> mel_gsteps, mel_goff; // per group: steps, offset into mel_wp
 
     std::map<int, FftTables> fft;              // keyed by NC
 
@@ -83,7 +109,12 @@ struct Plan {
     int32_t *d_mel_start = nullptr, *d_mel_cnt = nullptr, *d_mel_off = nullptr;
     CqtRow *d_rows = nullptr;
     cfloat *d_weights = nullptr;
+    CqtBlock *d_blocks = nullptr;
+    CqtGroup *d_cgroups = nullptr;
+    cfloat4 *d_weights4 = nullptr;
     CqtItem *d_items = nullptr;                // sorted by nfft so each kernel instantiation sees a contiguous slice
+    float *d_mel_wp = nullptr;
+    int32_t *d_mel_gsteps = nullptr, *d_mel_goff = nullptr;
     std::vector<void *> d_allocs;
 
     // optional per-kernel timing (amtfeat_profile_*): CUDA event pairs recorded around every launch of

@@ -23,8 +23,14 @@ from oracle import modules as om
 pytestmark = pytest.mark.gpu
 
 REL_L2_TOL = 1e-5
-DB_TOL_TOP = {'STFT': 1e-3, 'MelSpec': 1e-3, 'SignalPower': 1e-3, 'CQT': 5e-3, 'VQT': 5e-3, 'HCQT': 5e-2, 'HVQT': 5e-2}
-DB_TOL_ALL = {'STFT': 2e-2, 'MelSpec': 1e-2, 'SignalPower': 1e-3, 'CQT': 5e-2, 'VQT': 5e-2, 'HCQT': 0.5, 'HVQT': 0.5}
+DB_TOL_TOP = {'STFT': 1e-3, 'MelSpec': 1e-3, 'SignalPower': 1e-3, 'CQT': 5e-3, 'VQT': 5e-3, 'HCQT': 5e-3, 'HVQT': 5e-3}
+DB_TOL_ALL = {'STFT': 2e-2, 'MelSpec': 1e-2, 'SignalPower': 1e-3, 'CQT': 5e-2, 'VQT': 5e-2, 'HCQT': 5e-2, 'HVQT': 5e-2}
+# Harmonics that librosa early-downsamples by 4 or more in ONE resample call (eds >= 2, e.g. h = 0.5 of the HCQT) are
+# served from the shared cascaded 2:1 ladder (DESIGN.md "Known deviations" #1): identical in the pass band, but the
+# intermediate signal is truncated like librosa's own octave-to-octave steps, so the last ~1.5 s of those channels see a
+# slightly different end-of-signal transient.  They are checked with DB_TOL_TAIL there.
+DB_TOL_TAIL = 0.5
+TAIL_SECONDS = 1.5
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'golden_v1.npz')
 
 
@@ -91,7 +97,13 @@ def test_decibel_parity(idx):
     got = m.process_audio(y).cpu().numpy()
     want = o.process_audio(y)
     assert got.shape == want.shape
-    e_all, e_top = db_errors(name, got, want)
+    if name in ('HCQT', 'HVQT') and max(m.describe()['eds_ref']) >= 2:
+        tail = int(np.ceil(TAIL_SECONDS * sr / kw['hop_length']))
+        e_tail, _ = db_errors(name, got[..., -tail:], want[..., -tail:])
+        assert e_tail <= DB_TOL_TAIL, (name, 'tail', e_tail)
+        e_all, e_top = db_errors(name, got[..., :-tail], want[..., :-tail])
+    else:
+        e_all, e_top = db_errors(name, got, want)
     assert e_top <= DB_TOL_TOP[name], (name, e_top)
     assert e_all <= DB_TOL_ALL[name], (name, e_all)
     if name != 'SignalPower':
