@@ -466,7 +466,6 @@ static int build_vqt(Plan &p) {
     p.items.clear();
     p.item_kmax_true.clear();
     p.blocks.clear();
-    p.cgroups.clear();
     p.weights4.clear();
     for (auto &g : groups) {
         CqtItem it{};
@@ -477,58 +476,50 @@ static int build_vqt(Plan &p) {
         it.kmin = INT32_MAX;
         it.kmax = 0;
         const int NC = it.nfft / 2;
-        // pair adjacent rows of the same (harmonic, octave) run into blocks
-        std::vector<CqtBlock> blks;
-        std::vector<std::pair<const CqtRow *, const CqtRow *>> members;
+        // group up to four adjacent rows of the same (harmonic, octave) run into blocks
         const std::vector<CqtRow> &rs = g.second;
+        it.blk0 = (int32_t)p.blocks.size();
         for (size_t i = 0; i < rs.size();) {
-            const CqtRow *a = &rs[i], *b = nullptr;
-            if (i + 1 < rs.size() && rs[i + 1].chan == a->chan && rs[i + 1].bin == a->bin + 1) b = &rs[i + 1];
-            CqtBlock bl{};
-            bl.col0 = b ? std::min(a->col0, b->col0) : a->col0;
-            bl.chan_a = a->chan; bl.bin_a = a->bin; bl.inv_a = a->inv_len;
-            bl.chan_b = b ? b->chan : -1; bl.bin_b = b ? b->bin : 0; bl.inv_b = b ? b->inv_len : 0.f;
-            blks.push_back(bl);
-            members.push_back({a, b});
-            i += b ? 2 : 1;
-        }
-        it.grp0 = (int32_t)p.cgroups.size();
-        for (size_t b0 = 0; b0 < blks.size(); b0 += 16) {
-            CqtGroup cg{};
-            cg.blk0 = (int32_t)(p.blocks.size());
-            cg.nblk = (int32_t)std::min<size_t>(16, blks.size() - b0);
-            int steps = 0;
-            for (int j = 0; j < cg.nblk; ++j) {
-                const auto &m = members[b0 + j];
-                int end = m.first->col0 + m.first->cnt;
-                if (m.second) end = std::max(end, m.second->col0 + m.second->cnt);
-                steps = std::max(steps, end - blks[b0 + j].col0);
+            size_t n = 1;
+            while (n < 4 && i + n < rs.size() && rs[i + n].chan == rs[i].chan && rs[i + n].bin == rs[i].bin + (int)n) ++n;
+            CqtBlock4 bl{};
+            int lo = INT32_MAX, hi = 0;
+            for (size_t r = 0; r < n; ++r) {
+                lo = std::min(lo, rs[i + r].col0);
+                hi = std::max(hi, rs[i + r].col0 + rs[i + r].cnt);
             }
-            cg.steps = steps;
-            cg.woff = (int32_t)p.weights4.size();
-            p.weights4.resize(p.weights4.size() + (size_t)steps * 16, cfloat4{0, 0, 0, 0});
-            for (int j = 0; j < cg.nblk; ++j) {
-                const auto &m = members[b0 + j];
-                const int col0 = blks[b0 + j].col0;
-                for (int s = 0; s < steps; ++s) {
-                    cfloat4 &w = p.weights4[(size_t)cg.woff + (size_t)s * 16 + j];
-                    const int col = col0 + s;
-                    if (col >= m.first->col0 && col < m.first->col0 + m.first->cnt) {
-                        const cfloat v = p.weights[m.first->woff + (col - m.first->col0)];
-                        w.ar = v.x; w.ai = v.y;
-                    }
-                    if (m.second && col >= m.second->col0 && col < m.second->col0 + m.second->cnt) {
-                        const cfloat v = p.weights[m.second->woff + (col - m.second->col0)];
-                        w.br = v.x; w.bi = v.y;
+            hi = std::min(hi, NC + 1);
+            bl.col0 = lo;
+            bl.steps = hi - lo;
+            bl.woff = (int32_t)p.weights4.size();
+            bl.chan = rs[i].chan;
+            for (int r = 0; r < 4; ++r) {
+                bl.off[r] = r < (int)n ? rs[i + r].chan * p.F + rs[i + r].bin : -1;
+                bl.inv[r] = r < (int)n ? rs[i + r].inv_len : 0.f;
+            }
+            p.weights4.resize(p.weights4.size() + (size_t)bl.steps * 2, cfloat4{0, 0, 0, 0});
+            for (int st = 0; st < bl.steps; ++st) {
+                const int col = lo + st;
+                float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (size_t r = 0; r < n; ++r) {
+                    const CqtRow &rw = rs[i + r];
+                    if (col >= rw.col0 && col < rw.col0 + rw.cnt) {
+                        const cfloat v = p.weights[rw.woff + (col - rw.col0)];
+                        w[2 * r] = v.x;
+                        w[2 * r + 1] = v.y;
                     }
                 }
-                it.kmin = std::min(it.kmin, col0);
-                it.kmax = std::max(it.kmax, std::min(NC, col0 + steps - 1));
-                p.blocks.push_back(blks[b0 + j]);
+                p.weights4[(size_t)bl.woff + 2 * st] = cfloat4{w[0], w[1], w[2], w[3]};
+                p.weights4[(size_t)bl.woff + 2 * st + 1] = cfloat4{w[4], w[5], w[6], w[7]};
             }
-            p.cgroups.push_back(cg);
+            it.kmin = std::min(it.kmin, lo);
+            it.kmax = std::max(it.kmax, hi - 1);
+            p.blocks.push_back(bl);
+            i += n;
         }
-        it.ngrp = (int32_t)p.cgroups.size() - it.grp0;
+        it.nblk = (int32_t)p.blocks.size() - it.blk0;
+        it.woff0 = it.nblk ? p.blocks[it.blk0].woff : 0;
+        it.wcount = (int32_t)p.weights4.size() - it.woff0;
         int ktrue = 0;
         it.row0 = (int32_t)p.rows.size();
         for (const CqtRow &rw : rs) {
@@ -590,7 +581,7 @@ std::string describe(const Plan &p) {
     if (c.kind == AMTFEAT_MEL) o << ", \"mel_nnz\": " << p.mel_w.size();
     if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
         o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size()
-          << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_steps\": " << p.weights4.size() / 16 * 16 << ", \"eds_ref\": [";
+          << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_nnz\": " << p.weights4.size() * 2 << ", \"eds_ref\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_ref;
         o << "], \"eds_lib\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_lib;
@@ -598,7 +589,7 @@ std::string describe(const Plan &p) {
         for (size_t i = 0; i < p.items.size(); ++i) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
-              << ", \"rows\": " << it.nrows << ", \"groups\": " << it.ngrp << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
+              << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
         }
         o << "]";
     }

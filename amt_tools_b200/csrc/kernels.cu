@@ -405,13 +405,12 @@ struct CqtParams {
     const ClipMeta *meta;
     float *maxbuf;
     const CqtItem *items;
-    const CqtGroup *groups;
-    const CqtBlock *blocks;
+    const CqtBlock4 *blocks;
     const float4 *weights4;
     const CqtRow *rows;
     const float2 *weights;
     const float2 *tw1, *tw2;
-    int C, F, decibels, tile_floats, stage_groups, stage_rows;
+    int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off;
 };
 
 // Shared prologue of both CQT kernels: stage the level signal, run the warp FFT unit.
@@ -441,22 +440,26 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
     }
 }
 
-// Main kernel (n_fft >= 128).  Phase A: per-warp FFT + real-FFT split restricted to the band the item's rows touch,
-// D[t][k - kmin] left in the warps' scratch.  Phase B: every half-warp takes one group of 16 row blocks and one
-// chunk of 8 frames; a thread accumulates 2 rows x 8 frames in registers, so each weight fetch (one coalesced
-// 16-byte load) feeds 16 complex MACs and each D fetch feeds 2.
+// Main kernel (n_fft >= 128).
+// Phase A: per-warp FFT, then the real-FFT split restricted to the band [kmin, kmax] the item's rows touch; the band
+//          is written TRANSPOSED into Dbuf[k - kmin][frame] (frame fastest, pitch TT + 1), which aliases the audio tile.
+// Phase B: lanes run along frames, so every D fetch is a contiguous, conflict-free line; a group of FL lanes takes one
+//          block of up to 4 rows and streams its warp-uniform weights ([step][4 rows], two 16-byte loads per step):
+//          each D value feeds 4 complex MACs.  Results go through a staging tile (aliasing the FFT scratch) so that the
+//          global stores are T-contiguous.
 template <int NC>
 __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2;
-    constexpr int NCH = TT / 8;  // chunks of 8 frames
+    constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
+    constexpr int NSUB = kThreads / FL;         // lane groups per CTA
+    constexpr int NCHUNK = TT / FL;             // frame chunks per tile
+    constexpr int DP = TT + 1;                  // Dbuf pitch in float2 (odd: transposed writes are conflict free)
     extern __shared__ __align__(16) float smem[];
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
     float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
-    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH
-    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // tile_floats
-    float *s_stage = s_tile + p.tile_floats;                          // stage_groups * 32 rows * (TT + 1)
-    int *s_rowoff = reinterpret_cast<int *>(s_stage + p.stage_groups * 32 * (TT + 1));  // stage_groups * 32
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH; later the staging tile
+    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // audio tile; later Dbuf
     __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -468,8 +471,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
     cqt_fft_phase<NC>(p, it, cm, t0, s_tw1, s_tw2, s_scr, s_tile);
 
-    {   // real-FFT split on the band [kmin, kmax]
-        float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
+    // Phase-B layout of the combined [scratch | tile] region: staging tile + row offsets, then Dbuf, then the item's weights
+    float *s_stage = s_scr;
+    int *s_rowoff = reinterpret_cast<int *>(s_stage + p.stage_blocks * 4 * (TT + 1));
+    float2 *Dbuf = reinterpret_cast<float2 *>(s_scr + p.dbuf_off);
+    float4 *s_w = reinterpret_cast<float4 *>(s_scr + p.w_off);
+    {   // real-FFT split on the band, held in registers across the barrier that retires the scratch and the audio tile
+        const float2 *scr = reinterpret_cast<const float2 *>(s_scr) + warp * WP2;
         const int kb = it.kmax - it.kmin + 1;
         constexpr int JB = (NC + 1 + 31) / 32;
         float2 X[G][JB];
@@ -486,78 +494,68 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                     X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
                 }
             }
-        __syncwarp();
+        __syncthreads();
+        // stream the item's weights into shared memory (asynchronously, L1 bypass) while D is being written
+        {
+            const float4 *src = p.weights4 + it.woff0;
+            for (int i = tid; i < it.wcount; i += kThreads) {
+                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_w + i));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + i) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
             for (int j = 0; j < JB; ++j) {
                 const int kk = lane + 32 * j;
-                if (kk < kb) scr[g * S + kk] = X[g][j];
+                if (kk < kb) Dbuf[kk * DP + warp * G + g] = X[g][j];
             }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     }
     __syncthreads();
 
-    const float2 *D = reinterpret_cast<const float2 *>(s_scr);
     float *out = p.out + cm->out_off;
-    const int l16 = tid & 15;
-    for (int g0 = 0; g0 < it.ngrp; g0 += p.stage_groups) {
-        const int ng = min(p.stage_groups, it.ngrp - g0);
-        // output row offsets of this pass (row slot = 2 * (16 * group + block) + {a, b})
-        for (int rs = tid; rs < ng * 32; rs += kThreads) {
-            const CqtGroup cg = p.groups[it.grp0 + g0 + (rs >> 5)];
-            const int l = (rs >> 1) & 15;
-            int off = -1;
-            if (l < cg.nblk) {
-                const CqtBlock *bl = p.blocks + cg.blk0 + l;
-                const int chan = (rs & 1) ? bl->chan_b : bl->chan_a, bin = (rs & 1) ? bl->bin_b : bl->bin_a;
-                if (chan >= 0) off = chan * p.F + bin;
+    const int sub = tid / FL, lt = tid % FL;
+    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
+    for (int b0 = 0; b0 < it.nblk; b0 += p.stage_blocks) {
+        const int nb = min(p.stage_blocks, it.nblk - b0);
+        for (int rs = tid; rs < nb * 4; rs += kThreads) s_rowoff[rs] = p.blocks[it.blk0 + b0 + (rs >> 2)].off[rs & 3];
+        for (int w = sub; w < nb * NCHUNK; w += NSUB) {
+            const int bi = w / NCHUNK, ch = w % NCHUNK;
+            const CqtBlock4 *bl = p.blocks + it.blk0 + b0 + bi;
+            const int steps = bl->steps;
+            const float4 *wt = s_w + (bl->woff - it.woff0);
+            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 4
+            for (int s = 0; s < steps; ++s) {
+                const float2 d = Dp[s * DP];
+                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
+                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
+                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
+                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
+                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
+                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
+                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
+                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
+                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
             }
-            s_rowoff[rs] = off;
-        }
-        for (int hw = tid >> 4; hw < ng * NCH; hw += kThreads / 16) {
-            const int gi = hw / NCH, ch = hw % NCH;
-            const CqtGroup cg = p.groups[it.grp0 + g0 + gi];
-            if (l16 < cg.nblk) {
-                const CqtBlock bl = p.blocks[cg.blk0 + l16];
-                const float4 *w = p.weights4 + cg.woff + l16;
-                // frame f of the chunk sits at foff(f) float2 from Dp
-#define AMT_FOFF(f) (G >= 8 ? (f) * S : ((f) / G) * WP2 + ((f) % G) * S)
-                const int tb = ch * 8;
-                const float2 *Dp = D + (tb / G) * WP2 + (G >= 8 ? (tb % G) * S : 0) + (bl.col0 - it.kmin);
-                float2 a[8], b[8];
+            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
+                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
+            const int t = ch * FL + lt;
+            float *st = s_stage + (bi * 4) * (TT + 1) + t;
 #pragma unroll
-                for (int f = 0; f < 8; ++f) a[f] = b[f] = make_float2(0.f, 0.f);
-#pragma unroll 2
-                for (int s = 0; s < cg.steps; ++s) {
-                    const float4 wv = __ldg(w + s * 16);
+            for (int r = 0; r < 4; ++r) st[r * (TT + 1)] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
+            if (p.decibels) {
+                float vmax = (t0 + t < T) ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
 #pragma unroll
-                    for (int f = 0; f < 8; ++f) {
-                        const float2 d = Dp[AMT_FOFF(f) + s];
-                        a[f].x = fmaf(wv.x, d.x, a[f].x);
-                        a[f].x = fmaf(-wv.y, d.y, a[f].x);
-                        a[f].y = fmaf(wv.x, d.y, a[f].y);
-                        a[f].y = fmaf(wv.y, d.x, a[f].y);
-                        b[f].x = fmaf(wv.z, d.x, b[f].x);
-                        b[f].x = fmaf(-wv.w, d.y, b[f].x);
-                        b[f].y = fmaf(wv.z, d.y, b[f].y);
-                        b[f].y = fmaf(wv.w, d.x, b[f].y);
-                    }
-                }
-                float vmax = 0.f;
-                float *st = s_stage + (gi * 32 + 2 * l16) * (TT + 1) + tb;
-#pragma unroll
-                for (int f = 0; f < 8; ++f) {
-                    const float pa = fmaf(a[f].x, a[f].x, a[f].y * a[f].y) * bl.inv_a;
-                    const float pb = fmaf(b[f].x, b[f].x, b[f].y * b[f].y) * bl.inv_b;
-                    if (t0 + tb + f < T) vmax = fmaxf(vmax, fmaxf(pa, pb));
-                    st[f] = p.decibels ? db10(fmaxf(1e-10f, pa)) : sqrtf(pa);
-                    st[(TT + 1) + f] = p.decibels ? db10(fmaxf(1e-10f, pb)) : sqrtf(pb);
-                }
-                if (p.decibels) atomicMax(&s_max[bl.chan_a], __float_as_int(vmax));
+                for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
+                if (lt == 0) atomicMax(&s_max[bl->chan], __float_as_int(vmax));
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < ng * 32 * TT; idx += kThreads) {
+        for (int idx = tid; idx < nb * 4 * TT; idx += kThreads) {
             const int t = idx % TT, rs = idx / TT;
             const int off = s_rowoff[rs];
             if (off >= 0 && t0 + t < T) out[(long long)off * T + t0 + t] = s_stage[rs * (TT + 1) + t];
@@ -724,7 +722,6 @@ int upload_plan(Plan &p) {
     if ((rc = upload_vec(p, p.rows, &p.d_rows))) return rc;
     if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
     if ((rc = upload_vec(p, p.blocks, &p.d_blocks))) return rc;
-    if ((rc = upload_vec(p, p.cgroups, &p.d_cgroups))) return rc;
     if ((rc = upload_vec(p, p.weights4, &p.d_weights4))) return rc;
     if ((rc = upload_vec(p, p.mel_wp, &p.d_mel_wp))) return rc;
     if ((rc = upload_vec(p, p.mel_gsteps, &p.d_mel_gsteps))) return rc;
@@ -854,11 +851,12 @@ template <int NC>
 static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int batch, int maxT, cudaStream_t st) {
     using L = FftLayout<NC>;
     const int TT = kWarpsPerCta * L::G;
-    int maxhop = 0, maxrows = 0, maxgrp = 0;
+    int maxhop = 0, maxrows = 0, maxblk = 0, maxkb = 0;
     for (int i = item0; i < item0 + nitems; ++i) {
         maxhop = std::max(maxhop, p.items[i].hop);
         maxrows = std::max(maxrows, p.items[i].nrows);
-        maxgrp = std::max(maxgrp, p.items[i].ngrp);
+        maxblk = std::max(maxblk, p.items[i].nblk);
+        maxkb = std::max(maxkb, p.items[i].kmax - p.items[i].kmin + 1);
     }
     cp.tile_floats = tile_floats_for(TT, maxhop, 2 * NC);
     cp.items = p.d_items + item0;
@@ -867,21 +865,30 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
     dim3 grid((maxT + TT - 1) / TT, batch, nitems);
     static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
+    size_t smem;
     if (cqt_use_blocks<NC>()) {
-        cp.stage_groups = std::max(1, std::min(maxgrp, 4480 / (32 * (TT + 1))));
-        cp.stage_rows = cp.stage_groups * 32;
-        const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
-        if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
-        ProfScope ps(p, nm.c_str(), st);
-        cqt_kernel<(NC >= 64 ? NC : 64)><<<grid, kThreads, smem, st>>>(cp);
+        // phase B reuses the [FFT scratch | audio tile] region: staging tile + row offsets, Dbuf, the item's weights
+        const int scratch_floats = kWarpsPerCta * L::WARP_PITCH;
+        int maxw = 0;
+        for (int i = item0; i < item0 + nitems; ++i) maxw = std::max(maxw, p.items[i].wcount);
+        cp.stage_blocks = std::max(1, std::min(maxblk, 4096 / (4 * (TT + 1))));
+        cp.stage_rows = 0;
+        const int stage_floats = (cp.stage_blocks * 4 * (TT + 2) + 3) / 4 * 4;
+        const int dbuf_floats = (maxkb * (TT + 1) * 2 + 3) / 4 * 4;
+        cp.dbuf_off = stage_floats;
+        cp.w_off = stage_floats + dbuf_floats;
+        const int need = cp.w_off + maxw * 4;
+        cp.tile_floats = std::max(cp.tile_floats, (need - scratch_floats + 3) / 4 * 4);
+        smem = (size_t)(2 * NC + 2 * (NC + 2) + scratch_floats + cp.tile_floats) * sizeof(float);
     } else {
-        cp.stage_groups = 0;
+        cp.stage_blocks = 0;
         cp.stage_rows = std::max(1, std::min(maxrows, 3072 / (TT + 1)));
-        const size_t smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
-        if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
-        ProfScope ps(p, nm.c_str(), st);
-        cqt_small_kernel<(NC < 64 ? NC : 32)><<<grid, kThreads, smem, st>>>(cp);
+        smem = cqt_smem<NC>(cp.tile_floats, cp.stage_rows);
     }
+    if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+    ProfScope ps(p, nm.c_str(), st);
+    if (cqt_use_blocks<NC>()) cqt_kernel<(NC >= 64 ? NC : 64)><<<grid, kThreads, smem, st>>>(cp);
+    else cqt_small_kernel<(NC < 64 ? NC : 32)><<<grid, kThreads, smem, st>>>(cp);
     AMT_CUDA(cudaGetLastError());
     return AMTFEAT_OK;
 }
@@ -971,7 +978,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         CqtParams cp{};
         cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
         cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
-        cp.groups = p.d_cgroups; cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
+        cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
         cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
         size_t i0 = 0;
         while (i0 < p.items.size()) {

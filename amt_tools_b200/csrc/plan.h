@@ -40,25 +40,23 @@ struct CqtRow {
     int32_t woff;      // offset into the weight array
 };
 
-// Two adjacent rows of one (harmonic, octave) run, projected together so every FFT bin fetched from
-// shared memory feeds two complex MACs.  Row b is absent (chan_b < 0) for an odd-length run.
-struct CqtBlock {
-    int32_t col0;               // first FFT bin of the union band of both rows
-    int32_t chan_a, bin_a, chan_b, bin_b;
-    float inv_a, inv_b;         // 1 / length of each row (applied to the power)
-    int32_t pad_;
-};
-
-// 16 consecutive blocks: the unit of work of one half-warp.  Weights are stored [step][16 blocks] as
-// (re_a, im_a, re_b, im_b) so a half-warp's load of one step is one contiguous 256-byte line.
-struct CqtGroup {
-    int32_t blk0, nblk, steps, woff;
+// Up to four adjacent rows of one (harmonic, octave) run, projected together by the lanes that share a
+// frame: every FFT bin fetched from shared memory feeds four complex MACs, and the block's weights are a
+// warp-uniform stream of [step][4 rows] complex values (two 16-byte loads per step).
+struct CqtBlock4 {
+    int32_t col0;       // first FFT bin of the union band of the rows
+    int32_t steps;      // width of the union band (weights outside a row's own band are stored as zeros)
+    int32_t woff;       // offset into weights4, in float4 (2 float4 per step)
+    int32_t chan;       // output channel (harmonic index) of all rows of the block
+    int32_t off[4];     // chan * F + bin of each row, -1 if absent
+    float inv[4];       // 1 / length of each row (applied to the power)
 };
 
 // All rows that consume the FFT frames of one (ladder level, n_fft) pair.
 struct CqtItem {
-    int32_t level, nfft, hop, grp0, ngrp, kmin, kmax, nrows;
+    int32_t level, nfft, hop, blk0, nblk, kmin, kmax, nrows;
     int32_t row0, kmax_true;    // per-row tables (small-n_fft fallback kernel); last bin with a non-zero weight
+    int32_t woff0, wcount;      // the item's slice of weights4 (float4 units), staged into shared memory per CTA
 };
 
 struct cfloat4 {
@@ -94,8 +92,7 @@ struct Plan {
     std::vector<float> taps;                   // 2:1 decimator, includes the sqrt(2) of `scale=True`
     std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
     std::vector<cfloat> weights;               // per-row weights (host only)
-    std::vector<CqtBlock> blocks;
-    std::vector<CqtGroup> cgroups;
+    std::vector<CqtBlock4> blocks;
     std::vector<cfloat4> weights4;
     std::vector<CqtItem> items;
     std::vector<int32_t> item_kmax_true;       // last FFT bin with a non-zero weight, per item (describe / tests)
@@ -109,8 +106,7 @@ struct Plan {
     int32_t *d_mel_start = nullptr, *d_mel_cnt = nullptr, *d_mel_off = nullptr;
     CqtRow *d_rows = nullptr;
     cfloat *d_weights = nullptr;
-    CqtBlock *d_blocks = nullptr;
-    CqtGroup *d_cgroups = nullptr;
+    CqtBlock4 *d_blocks = nullptr;
     cfloat4 *d_weights4 = nullptr;
     CqtItem *d_items = nullptr;                // sorted by nfft so each kernel instantiation sees a contiguous slice
     float *d_mel_wp = nullptr;

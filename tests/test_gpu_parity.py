@@ -127,6 +127,10 @@ def test_golden_fixtures():
         if kw.get('decibels', True):
             e_all, e_top = db_errors(name, got, want)
             assert e_top <= DB_TOL_TOP[name] and e_all <= DB_TOL_ALL[name], (case, e_all, e_top)
+        elif case == 'hcqt_lin':
+            # channel 0 (h = 0.5, early-downsampled by 4) on a 1 s clip is all "tail": see DB_TOL_TAIL above
+            assert rel_l2(got[1:], want[1:]) <= REL_L2_TOL, case
+            assert rel_l2(got[0], want[0]) <= 5e-4, case
         else:
             assert rel_l2(got, want) <= REL_L2_TOL, case
 

@@ -51,3 +51,37 @@ def main(rep, kernel_idx=0, top=25):
 
 if __name__ == '__main__':
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else 25)
+
+
+def conflicts(rep, kernel_idx=0, top=20):
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
+                         capture_output=True, text=True).stdout
+    blocks, cur = [], None
+    for row in csv.reader(out.splitlines()):
+        if row and row[0] == 'Kernel Name':
+            cur = {'name': row[1], 'hdr': None, 'rows': []}
+            blocks.append(cur)
+        elif cur is not None and row and row[0] == 'Address':
+            cur['hdr'] = row
+        elif cur is not None and cur['hdr'] and row:
+            cur['rows'].append(row)
+    b = blocks[kernel_idx]
+    h = b['hdr']
+    wi, xi, ii = h.index('L1 Wavefronts Shared'), h.index('L1 Wavefronts Shared Excessive'), h.index('L1 Wavefronts Shared Ideal')
+    tot = sum(int(r[wi] or 0) for r in b['rows'])
+    exc = sum(int(r[xi] or 0) for r in b['rows'])
+    print('shared wavefronts', tot, 'excessive', exc)
+    agg = {}
+    for r in b['rows']:
+        if int(r[wi] or 0) > 0:
+            op = r[1].split()[0] if not r[1].startswith('@') else r[1].split()[1]
+            a = agg.setdefault(op, [0, 0])
+            a[0] += int(r[wi]); a[1] += int(r[xi] or 0)
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print('  %-12s wavefronts %10d excessive %10d' % (k, v[0], v[1]))
+    for r in sorted(b['rows'], key=lambda r: -int(r[xi] or 0))[:top]:
+        print('%10s %10s  %s' % (r[wi], r[xi], r[1][:80]))
+
+
+if __name__ == '__main__' and len(sys.argv) > 4 and sys.argv[4] == 'conflicts':
+    conflicts(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))
