@@ -224,22 +224,61 @@ static void build_mel(Plan &p) {
             p.mel_w.insert(p.mel_w.end(), row.begin() + first, row.begin() + last + 1);
         }
     }
-    // padded, lane-major copy: filters m = 32 g + lane run in lockstep for steps[g] = max count in the group
-    const int ngroups = (n_mels + 31) / 32;
+    // segment form (see plan.h): every FFT bin has at most two non-zero filters, m and m + 1
+    const int nseg = n_mels + 1;
+    std::vector<int> seg_of(nb, -1);
+    std::vector<float> up(nb, 0.f), down(nb, 0.f);
+    {
+        std::vector<std::vector<std::pair<int, float>>> nz(nb);
+        for (int i = 0; i < n_mels; ++i)
+            for (int j = 0; j < p.mel_cnt[i]; ++j) {
+                float w = p.mel_w[p.mel_off[i] + j];
+                if (w != 0.f) nz[p.mel_start[i] + j].push_back({i, w});
+            }
+        for (int k = 0; k < nb; ++k) {
+            const double fk = (double)k * c.sample_rate / (double)c.n_fft;
+            if (nz[k].size() == 2 && nz[k][1].first == nz[k][0].first + 1) {
+                seg_of[k] = nz[k][1].first;
+                up[k] = nz[k][1].second;
+                down[k] = nz[k][0].second;
+            } else if (nz[k].size() == 1) {
+                const int i = nz[k][0].first;
+                if (fk < mel_f[i + 1]) { seg_of[k] = i; up[k] = nz[k][0].second; }
+                else { seg_of[k] = i + 1; down[k] = nz[k][0].second; }
+            } else if (!nz[k].empty()) {
+                p.mel_ww.clear();
+                p.mel_seg_start.clear();
+                return;  // build_plan_tables reports the unsupported filterbank
+            }
+        }
+    }
+    // bins with no filter inherit the previous segment with zero weights so that segments stay contiguous
+    int cur = 0;
+    for (int k = 0; k < nb; ++k) {
+        if (seg_of[k] < 0) seg_of[k] = cur;
+        if (seg_of[k] < cur) { p.mel_ww.clear(); p.mel_seg_start.clear(); return; }
+        cur = seg_of[k];
+    }
+    p.mel_seg_start.assign(nseg, nb);
+    std::vector<int> seg_cnt(nseg, 0);
+    for (int k = nb - 1; k >= 0; --k) { p.mel_seg_start[seg_of[k]] = k; seg_cnt[seg_of[k]]++; }
+    for (int sgi = 0; sgi < nseg; ++sgi) if (seg_cnt[sgi] == 0) p.mel_seg_start[sgi] = 0;
+    const int ngroups = (nseg + 31) / 32;
     p.mel_gsteps.assign(ngroups, 0);
     p.mel_goff.assign(ngroups, 0);
-    p.mel_wp.clear();
+    p.mel_ww.clear();
     for (int gidx = 0; gidx < ngroups; ++gidx) {
         int steps = 0;
-        for (int l = 0; l < 32 && 32 * gidx + l < n_mels; ++l) steps = std::max(steps, p.mel_cnt[32 * gidx + l]);
-        steps = (steps + 1) / 2 * 2;  // the kernel unrolls by two
+        for (int l = 0; l < 32 && 32 * gidx + l < nseg; ++l) steps = std::max(steps, seg_cnt[32 * gidx + l]);
         p.mel_gsteps[gidx] = steps;
-        p.mel_goff[gidx] = (int32_t)p.mel_wp.size();
-        p.mel_wp.resize(p.mel_wp.size() + (size_t)steps * 32, 0.f);
-        for (int l = 0; l < 32 && 32 * gidx + l < n_mels; ++l) {
-            const int m = 32 * gidx + l;
-            for (int j = 0; j < p.mel_cnt[m]; ++j)
-                p.mel_wp[(size_t)p.mel_goff[gidx] + (size_t)j * 32 + l] = p.mel_w[p.mel_off[m] + j];
+        p.mel_goff[gidx] = (int32_t)p.mel_ww.size();
+        p.mel_ww.resize(p.mel_ww.size() + (size_t)std::max(steps, 1) * 32, cfloat{0.f, 0.f});
+        for (int l = 0; l < 32 && 32 * gidx + l < nseg; ++l) {
+            const int sgi = 32 * gidx + l;
+            for (int j = 0; j < seg_cnt[sgi]; ++j) {
+                const int k = p.mel_seg_start[sgi] + j;
+                p.mel_ww[(size_t)p.mel_goff[gidx] + (size_t)j * 32 + l] = cfloat{up[k], down[k]};
+            }
         }
     }
 }
@@ -557,6 +596,7 @@ int build_plan_tables(Plan &p) {
             if (c.kind == AMTFEAT_MEL) {
                 if (c.n_mels <= 0) { set_error("n_mels must be positive"); return AMTFEAT_ERR_INVALID; }
                 build_mel(p);
+                if (p.mel_ww.empty()) { set_error("mel filterbank is not a chain of overlapping triangles (n_mels too large for n_fft?)"); return AMTFEAT_ERR_INVALID; }
                 p.F = c.n_mels;
             } else {
                 p.F = c.n_fft / 2 + 1;

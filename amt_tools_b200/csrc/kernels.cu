@@ -94,24 +94,34 @@ struct StftParams {
     float *maxbuf;
     const float *window;
     const float2 *tw1, *tw2;
-    const int *mel_start, *mel_gsteps, *mel_goff;
-    const float *mel_wp;
+    const int *mel_seg_start, *mel_gsteps, *mel_goff;
+    const float2 *mel_ww;
     int hop, pad, n_mels, decibels;
-    int tile_floats;
 };
 
 constexpr int MODE_STFT = 0, MODE_MEL = 1;
 
+// Input point n (samples 2n, 2n + 1) of the frame that starts at sample s0 of a clip of `len` samples, zero outside the
+// clip (this realises centre / frame padding without a padded copy).  Coalesced straight from global memory (the 4x
+// frame overlap is served by L1 / L2); `interior` (warp-uniform) skips the bounds checks.
+__device__ __forceinline__ float2 load_pair(const float *__restrict__ src, long long len, long long s0, int n, bool interior,
+                                            bool vec_ok) {
+    const long long i = s0 + 2 * n;
+    if (interior && vec_ok) return __ldg(reinterpret_cast<const float2 *>(src + i));
+    float2 v;
+    v.x = (i >= 0 && i < len) ? __ldg(src + i) : 0.f;
+    v.y = (i + 1 >= 0 && i + 1 < len) ? __ldg(src + i + 1) : 0.f;
+    return v;
+}
+
 template <int NC, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     using L = FftLayout<NC>;
-    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, PP = NC + 1, NFFT = 2 * NC;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, PT = TT + 1, NFFT = 2 * NC;
     extern __shared__ __align__(16) float smem[];
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                // NC
     float2 *s_tw2 = s_tw1 + NC;                                      // NC/2 (k = 0 .. NC/2 - 1)
-    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC / 2);        // 8 * WARP_PITCH
-    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;            // tile_floats
-    float *s_stage = s_tile + p.tile_floats;                         // MEL: n_mels * (TT + 1)
+    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC / 2);        // 8 * WARP_PITCH; later Pbuf[k][frame] (+ mel staging)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
@@ -121,28 +131,26 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
 
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i < NC / 2; i += kThreads) s_tw2[i] = p.tw2[i];
-    int shift, fstride;
-    load_tile(s_tile, p.audio + cm->in_off, cm->n, (long long)t0 * p.hop - p.pad, p.hop, NFFT, TT, tid, shift, fstride);
     __syncthreads();
 
     float2 *scr = reinterpret_cast<float2 *>(s_scr + warp * L::WARP_PITCH);
-    const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
-    const bool vec_ok = ((shift | fstride) & 1) == 0;
-    if (vec_ok) {
+    {
+        const float *src = p.audio + cm->in_off;
+        const long long len = cm->n;
+        const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
+        const long long sw0 = (long long)(t0 + warp * G) * p.hop - p.pad;            // first frame of this warp
+        const bool interior = sw0 >= 0 && sw0 + (long long)(G - 1) * p.hop + NFFT <= len;
+        const bool vec_ok = ((p.hop | p.pad) & 1) == 0;
         warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
-            const float2 x = *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+            const float2 x = load_pair(src, len, sw0 + (long long)g * p.hop, n, interior, vec_ok);
             const float2 w = __ldg(win2 + n);
             return make_float2(x.x * w.x, x.y * w.y);
         });
-    } else {
-        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
-            const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
-            const float2 w = __ldg(win2 + n);
-            return make_float2(x[0] * w.x, x[1] * w.y);
-        });
     }
 
-    // real-FFT split -> power spectrum, kept in this warp's scratch as P[g][0..NC]
+    // real-FFT split -> power spectrum in registers; after the barrier (scratch retired) it is written TRANSPOSED as
+    // Pbuf[k][frame] (frame fastest, odd pitch) so both the store below and the consumers are conflict free
+    float *Pbuf = s_scr;
     {
         float pw[16][2];
 #pragma unroll
@@ -161,41 +169,54 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
             const float2 A = scr[lane * S + NC / 2];
             pmid = fmaf(A.x, A.x, A.y * A.y);
         }
-        __syncwarp();
-        float *P = reinterpret_cast<float *>(scr);
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int q = lane + 32 * j;
             const int g = q / (NC / 2), k = q % (NC / 2);
-            P[g * PP + k] = pw[j][0];
-            P[g * PP + NC - k] = pw[j][1];
+            Pbuf[k * PT + warp * G + g] = pw[j][0];
+            Pbuf[(NC - k) * PT + warp * G + g] = pw[j][1];
         }
-        if (lane < G) P[lane * PP + NC / 2] = pmid;
-        __syncwarp();
+        if (lane < G) Pbuf[(NC / 2) * PT + warp * G + lane] = pmid;
     }
+    __syncthreads();
 
     float vmax = 0.f;
     float *out = p.out + cm->out_off;
     if (MODE == MODE_MEL) {
-        // sparse mel projection: filters 32 grp + lane advance in lockstep over the padded, lane-major weights
-        const float *P = reinterpret_cast<const float *>(scr);
-        const int ngroups = (p.n_mels + 31) >> 5;
-#pragma unroll 1
-        for (int g = 0; g < G; ++g) {
-#pragma unroll 1
-            for (int grp = 0; grp < ngroups; ++grp) {
-                const int m = grp * 32 + lane;
-                const bool active = m < p.n_mels;
-                const int steps = __ldg(p.mel_gsteps + grp);
-                const float *w = p.mel_wp + __ldg(p.mel_goff + grp) + lane;
-                const float *pp = P + g * PP + (active ? __ldg(p.mel_start + m) : 0);
-                float acc0 = 0.f, acc1 = 0.f;
+        // Sparse mel projection, segment form: FFT bin k lies between two mel centres and feeds exactly the rising slope
+        // of filter seg(k) and the falling slope of filter seg(k) - 1, so every power value is read once:
+        //   U[s] = sum_{k in segment s} up_k P[k],  V[s] = sum down_k P[k],  mel[m] = U[m] + V[m + 1].
+        // One thread per (segment, chunk of 8 frames); the (up, down) weights are padded lane-major per group of 32 segments.
+        float *s_U = Pbuf + (NC + 1) * PT, *s_V = s_U + (p.n_mels + 1) * PT;
+        const int nseg = p.n_mels + 1, ngroups = (nseg + 31) >> 5;
+        constexpr int NCHUNK = TT / 8;
+        for (int w = warp; w < ngroups * NCHUNK; w += kWarpsPerCta) {
+            const int grp = w / NCHUNK, ch = w % NCHUNK;
+            const int sgm = grp * 32 + lane;
+            const int steps = __ldg(p.mel_gsteps + grp);
+            const float2 *ww = p.mel_ww + __ldg(p.mel_goff + grp) + lane;
+            const int k0 = sgm < nseg ? __ldg(p.mel_seg_start + sgm) : 0;
+            float u[8], v[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) u[f] = v[f] = 0.f;
 #pragma unroll 2
-                for (int j = 0; j < steps; j += 2) {
-                    acc0 = fmaf(__ldg(w + j * 32), pp[j], acc0);
-                    acc1 = fmaf(__ldg(w + j * 32 + 32), pp[j + 1], acc1);
+            for (int j = 0; j < steps; ++j) {
+                const float2 wv = __ldg(ww + j * 32);
+                const float *pp = Pbuf + min(k0 + j, NC) * PT + ch * 8;
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    const float x = pp[f];
+                    u[f] = fmaf(wv.x, x, u[f]);
+                    v[f] = fmaf(wv.y, x, v[f]);
                 }
-                if (active) s_stage[m * (TT + 1) + warp * G + g] = acc0 + acc1;
+            }
+            if (sgm < nseg) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) {
+                    s_U[sgm * PT + ch * 8 + f] = u[f];
+                    s_V[sgm * PT + ch * 8 + f] = v[f];
+                }
             }
         }
         __syncthreads();
@@ -203,18 +224,17 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
         for (int idx = tid; idx < total; idx += kThreads) {
             const int t = idx % TT, m = idx / TT;
             if (t0 + t < T) {
-                const float v = s_stage[m * (TT + 1) + t];
+                const float v = s_U[m * PT + t] + s_V[(m + 1) * PT + t];
                 vmax = fmaxf(vmax, v);
                 out[(long long)m * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : v;
             }
         }
     } else {
-        __syncthreads();
         constexpr int total = (NC + 1) * TT;
         for (int idx = tid; idx < total; idx += kThreads) {
             const int t = idx % TT, k = idx / TT;
             if (t0 + t < T) {
-                const float v = s_scr[(t / G) * L::WARP_PITCH + (t % G) * PP + k];
+                const float v = Pbuf[k * PT + t];
                 vmax = fmaxf(vmax, v);
                 out[(long long)k * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v);
             }
@@ -676,11 +696,12 @@ template <typename Tp> static int upload_vec(Plan &p, const std::vector<Tp> &h, 
     return AMTFEAT_OK;
 }
 
-template <int NC> static size_t stft_smem(int tile_floats, int n_mels, bool mel) {
+template <int NC> static size_t stft_smem(int n_mels, bool mel) {
     using L = FftLayout<NC>;
-    size_t fl = 2 * NC + NC + (size_t)kWarpsPerCta * L::WARP_PITCH + tile_floats;
-    if (mel) fl += (size_t)n_mels * (kWarpsPerCta * L::G + 1);
-    return fl * sizeof(float);
+    const size_t PT = kWarpsPerCta * L::G + 1;
+    size_t region = (size_t)kWarpsPerCta * L::WARP_PITCH;                                  // FFT scratch ...
+    region = std::max(region, (size_t)(NC + 1) * PT + (mel ? 2 * (size_t)(n_mels + 1) * PT : 0));  // ... reused as Pbuf + mel staging
+    return (2 * NC + NC + region) * sizeof(float);
 }
 template <int NC> static size_t cqt_smem(int tile_floats, int stage_rows) {
     using L = FftLayout<NC>;
@@ -723,7 +744,8 @@ int upload_plan(Plan &p) {
     if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
     if ((rc = upload_vec(p, p.blocks, &p.d_blocks))) return rc;
     if ((rc = upload_vec(p, p.weights4, &p.d_weights4))) return rc;
-    if ((rc = upload_vec(p, p.mel_wp, &p.d_mel_wp))) return rc;
+    if ((rc = upload_vec(p, p.mel_ww, &p.d_mel_ww))) return rc;
+    if ((rc = upload_vec(p, p.mel_seg_start, &p.d_mel_seg_start))) return rc;
     if ((rc = upload_vec(p, p.mel_gsteps, &p.d_mel_gsteps))) return rc;
     if ((rc = upload_vec(p, p.mel_goff, &p.d_mel_goff))) return rc;
     if ((rc = upload_vec(p, p.items, &p.d_items))) return rc;
@@ -837,8 +859,8 @@ static int launch_stft(const Plan &p, const StftParams &sp, int batch, int maxT,
     using L = FftLayout<NC>;
     const int TT = kWarpsPerCta * L::G;
     const bool mel = p.cfg.kind == AMTFEAT_MEL;
-    const size_t smem = stft_smem<NC>(sp.tile_floats, sp.n_mels, mel);
-    if (smem > 227 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
+    const size_t smem = stft_smem<NC>(sp.n_mels, mel);
+    if (smem > 227 * 1024) { set_error("n_mels too large for this n_fft (shared-memory staging)"); return AMTFEAT_ERR_INVALID; }
     dim3 grid((maxT + TT - 1) / TT, batch);
     ProfScope ps(p, mel ? "stft_kernel_mel" : "stft_kernel_mag", st);
     if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);
@@ -933,9 +955,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         StftParams sp{};
         sp.audio = d_audio; sp.out = d_out; sp.meta = d_meta; sp.maxbuf = d_max; sp.window = p.d_window;
         sp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1); sp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
-        sp.mel_start = p.d_mel_start; sp.mel_gsteps = p.d_mel_gsteps; sp.mel_goff = p.d_mel_goff; sp.mel_wp = p.d_mel_wp;
+        sp.mel_seg_start = p.d_mel_seg_start; sp.mel_gsteps = p.d_mel_gsteps; sp.mel_goff = p.d_mel_goff;
+        sp.mel_ww = reinterpret_cast<const float2 *>(p.d_mel_ww);
         sp.hop = c.hop_length; sp.pad = c.center ? c.n_fft / 2 : 0; sp.n_mels = c.n_mels; sp.decibels = c.decibels;
-        sp.tile_floats = tile_floats_for(kWarpsPerCta * (1024 / NC), c.hop_length, c.n_fft);
         switch (NC) {
             case 1024: rc = launch_stft<1024>(p, sp, batch, maxT, st); break;
             case 512: rc = launch_stft<512>(p, sp, batch, maxT, st); break;

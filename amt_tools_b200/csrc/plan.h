@@ -96,8 +96,11 @@ struct Plan {
     std::vector<cfloat4> weights4;
     std::vector<CqtItem> items;
     std::vector<int32_t> item_kmax_true;       // last FFT bin with a non-zero weight, per item (describe / tests)
-    std::vector<float> mel_wp;                 // mel weights, padded [group of 32 filters][step][lane]
-    std::vector<int32_t> mel_gsteps, mel_goff; // per group: steps, offset into mel_wp
+    // mel projection in segment form: FFT bin k feeds the rising slope of filter seg(k) and the falling slope of
+    // filter seg(k) - 1.  mel_ww holds (up, down) per bin, padded lane-major [group of 32 segments][step][lane].
+    std::vector<int32_t> mel_seg_start;        // first FFT bin of each of the n_mels + 1 segments
+    std::vector<cfloat> mel_ww;
+    std::vector<int32_t> mel_gsteps, mel_goff; // per group: steps, offset into mel_ww
 
     std::map<int, FftTables> fft;              // keyed by NC
 
@@ -109,7 +112,8 @@ struct Plan {
     CqtBlock4 *d_blocks = nullptr;
     cfloat4 *d_weights4 = nullptr;
     CqtItem *d_items = nullptr;                // sorted by nfft so each kernel instantiation sees a contiguous slice
-    float *d_mel_wp = nullptr;
+    cfloat *d_mel_ww = nullptr;
+    int32_t *d_mel_seg_start = nullptr;
     int32_t *d_mel_gsteps = nullptr, *d_mel_goff = nullptr;
     std::vector<void *> d_allocs;
 

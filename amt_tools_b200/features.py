@@ -188,27 +188,46 @@ class FeatureModule(object):
                 buf[o:o + n].copy_(self._to_device_1d(c), non_blocking=True)
         return buf, offsets, lengths
 
-    def _run(self, buf, offsets, lengths):
-        """Launch the native path on the current stream; returns one tensor per clip."""
+    def _batch_layout(self, lengths):
+        """Output shapes / offsets / workspace size for a batch with these clip lengths (cached: batches repeat)."""
+        key = tuple(lengths)
+        cache = self.__dict__.setdefault('_layout_cache', {})
+        lay = cache.get(key)
+        if lay is None:
+            shapes = [self._out_shape(n) for n in lengths]
+            sizes = [int(np.prod(s)) for s in shapes]
+            out_offsets, total = [], 0
+            for sz in sizes:
+                out_offsets.append(total)
+                total += sz
+            n_arr = _lib.i64_array(lengths)
+            ws_bytes = int(_lib.lib.amtfeat_workspace_bytes(self._dev_plan.handle, len(lengths), n_arr)) if total else 0
+            lay = (shapes, sizes, out_offsets, _lib.i64_array(out_offsets), n_arr, ws_bytes, total)
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = lay
+        return lay
+
+    def _launch(self, buf, offsets, lengths):
+        """Enqueue the native path on the current stream; returns the flat output buffer and the batch layout."""
         plan = self._dev_plan
-        shapes = [self._out_shape(n) for n in lengths]
-        sizes = [int(np.prod(s)) for s in shapes]
-        out_offsets, total = [], 0
-        for s in sizes:
-            out_offsets.append(total)
-            total += s
+        lay = self._batch_layout(lengths)
+        shapes, sizes, out_offsets, out_arr, n_arr, ws_bytes, total = lay
         with torch.cuda.device(self.device):
             out = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
             if total:
-                n_arr = _lib.i64_array(lengths)
-                ws_bytes = int(_lib.lib.amtfeat_workspace_bytes(plan.handle, len(lengths), n_arr))
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
                 stream = torch.cuda.current_stream(self.device).cuda_stream
-                _lib.check(_lib.lib.amtfeat_process(plan.handle, buf.data_ptr(), _lib.i64_array(offsets), n_arr,
-                                                    _lib.i64_array(out_offsets), len(lengths), out.data_ptr(),
-                                                    ws.data_ptr(), ws_bytes, stream))
+                in_arr = _lib.i64_array(offsets) if isinstance(offsets, (list, tuple)) else offsets
+                _lib.check(_lib.lib.amtfeat_process(plan.handle, buf.data_ptr(), in_arr, n_arr, out_arr,
+                                                    len(lengths), out.data_ptr(), ws.data_ptr(), ws_bytes, stream))
                 # the caching allocator keeps `ws` / `buf` alive for this stream's pending work
-        return [out[o:o + s].view(shape) for o, s, shape in zip(out_offsets, sizes, shapes)]
+        return out, lay
+
+    def _run(self, buf, offsets, lengths):
+        """Launch and return one tensor per clip."""
+        out, (shapes, sizes, out_offsets, _, _, _, _) = self._launch(buf, offsets, lengths)
+        return [out[o:o + sz].view(shape) for o, sz, shape in zip(out_offsets, sizes, shapes)]
 
     def _finish(self, t):
         return t.cpu().numpy() if self.output == 'numpy' else t
@@ -225,7 +244,14 @@ class FeatureModule(object):
             B, N = int(audio.shape[0]), int(audio.shape[1])
             if isinstance(audio, torch.Tensor) and audio.is_cuda and audio.dtype == torch.float32 \
                     and audio.is_contiguous() and N % 4 == 0 and audio.data_ptr() % 16 == 0:
-                outs = self._run(audio.reshape(-1), [b * N for b in range(B)], [N] * B)
+                offs = self.__dict__.setdefault('_uniform_offsets', {})
+                if (B, N) not in offs:
+                    offs[(B, N)] = _lib.i64_array([b * N for b in range(B)])
+                out, lay = self._launch(audio.reshape(-1), offs[(B, N)], [N] * B)
+                shape, per = lay[0][0], lay[1][0]
+                if per:     # equal-length clips are written back to back: one (B, ...) tensor, no copy
+                    return self._finish(out[:B * per].view((B,) + shape))
+                outs = [out[:0].view(shape) for _ in range(B)]
             else:
                 buf, offsets, lengths = self._pack([audio[b] for b in range(B)])
                 outs = self._run(buf, offsets, lengths)
