@@ -96,7 +96,7 @@ struct StftParams {
     const float2 *tw1, *tw2;
     const int *mel_seg_start, *mel_gsteps, *mel_goff;
     const float2 *mel_ww;
-    int hop, pad, n_mels, decibels;
+    int hop, pad, n_mels, decibels, tile_floats, scr_floats;
 };
 
 constexpr int MODE_STFT = 0, MODE_MEL = 1;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                // NC
     float2 *s_tw2 = s_tw1 + NC;                                      // NC/2 (k = 0 .. NC/2 - 1)
     float *s_scr = reinterpret_cast<float *>(s_tw2 + NC / 2);        // 8 * WARP_PITCH; later Pbuf[k][frame] (+ mel staging)
+    float *s_tile = s_scr + p.scr_floats;                            // audio tile
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
@@ -131,21 +132,27 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
 
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i < NC / 2; i += kThreads) s_tw2[i] = p.tw2[i];
+    int shift, fstride;
+    load_tile(s_tile, p.audio + cm->in_off, cm->n, (long long)t0 * p.hop - p.pad, p.hop, NFFT, TT, tid, shift, fstride);
     __syncthreads();
 
     float2 *scr = reinterpret_cast<float2 *>(s_scr + warp * L::WARP_PITCH);
     {
-        const float *src = p.audio + cm->in_off;
-        const long long len = cm->n;
         const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
-        const long long sw0 = (long long)(t0 + warp * G) * p.hop - p.pad;            // first frame of this warp
-        const bool interior = sw0 >= 0 && sw0 + (long long)(G - 1) * p.hop + NFFT <= len;
-        const bool vec_ok = ((p.hop | p.pad) & 1) == 0;
-        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
-            const float2 x = load_pair(src, len, sw0 + (long long)g * p.hop, n, interior, vec_ok);
-            const float2 w = __ldg(win2 + n);
-            return make_float2(x.x * w.x, x.y * w.y);
-        });
+        const bool vec_ok = ((shift | fstride) & 1) == 0;
+        if (vec_ok) {
+            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                const float2 x = *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+                const float2 w = __ldg(win2 + n);
+                return make_float2(x.x * w.x, x.y * w.y);
+            });
+        } else {
+            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
+                const float2 w = __ldg(win2 + n);
+                return make_float2(x[0] * w.x, x[1] * w.y);
+            });
+        }
     }
 
     // real-FFT split -> power spectrum in registers; after the barrier (scratch retired) it is written TRANSPOSED as
@@ -334,8 +341,10 @@ __global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict
 constexpr int kDecR = 16;                       // consecutive outputs per thread (register sliding window)
 constexpr int kDecTile = kThreads * kDecR;      // outputs per CTA
 
-// Skewed shared-memory index: 4 extra floats per 32 so that 16-byte loads at a 64-byte lane stride are conflict free.
-__device__ __forceinline__ int dec_phys(int i) { return i + ((i >> 5) << 2); }
+// Skewed shared-memory index: 4 extra floats per 16.  A thread's window starts at 16 * lane + c, i.e. 16-byte quad
+// 4 * lane + c / 4; with the skew the quad becomes 5 * lane + const (mod 8 bank groups), a bijection for every
+// alignment c, so the 16-byte loads of a quarter warp never collide.
+__device__ __forceinline__ int dec_phys(int i) { return i + ((i >> 4) << 2); }
 
 __host__ __device__ inline int dec_front_pad(int D) { return ((((7 - D) % 4) + 4) % 4) + 8; }
 __host__ __device__ inline int dec_jtot(int D) { return (D + 1 + 7) / 8 * 8; }
@@ -696,12 +705,12 @@ template <typename Tp> static int upload_vec(Plan &p, const std::vector<Tp> &h, 
     return AMTFEAT_OK;
 }
 
-template <int NC> static size_t stft_smem(int n_mels, bool mel) {
+template <int NC> static size_t stft_scr_floats(int n_mels, bool mel) {
     using L = FftLayout<NC>;
     const size_t PT = kWarpsPerCta * L::G + 1;
     size_t region = (size_t)kWarpsPerCta * L::WARP_PITCH;                                  // FFT scratch ...
     region = std::max(region, (size_t)(NC + 1) * PT + (mel ? 2 * (size_t)(n_mels + 1) * PT : 0));  // ... reused as Pbuf + mel staging
-    return (2 * NC + NC + region) * sizeof(float);
+    return (region + 3) / 4 * 4;
 }
 template <int NC> static size_t cqt_smem(int tile_floats, int stage_rows) {
     using L = FftLayout<NC>;
@@ -855,12 +864,15 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
 }
 
 template <int NC>
-static int launch_stft(const Plan &p, const StftParams &sp, int batch, int maxT, cudaStream_t st) {
+static int launch_stft(const Plan &p, const StftParams &sp_in, int batch, int maxT, cudaStream_t st) {
     using L = FftLayout<NC>;
     const int TT = kWarpsPerCta * L::G;
     const bool mel = p.cfg.kind == AMTFEAT_MEL;
-    const size_t smem = stft_smem<NC>(sp.n_mels, mel);
-    if (smem > 227 * 1024) { set_error("n_mels too large for this n_fft (shared-memory staging)"); return AMTFEAT_ERR_INVALID; }
+    StftParams sp = sp_in;
+    sp.scr_floats = (int)stft_scr_floats<NC>(sp.n_mels, mel);
+    sp.tile_floats = tile_floats_for(TT, sp.hop, 2 * NC);
+    const size_t smem = (size_t)(2 * NC + NC + sp.scr_floats + sp.tile_floats) * sizeof(float);
+    if (smem > 227 * 1024) { set_error("hop_length / n_mels too large for the shared-memory tiles of this n_fft"); return AMTFEAT_ERR_INVALID; }
     dim3 grid((maxT + TT - 1) / TT, batch);
     ProfScope ps(p, mel ? "stft_kernel_mel" : "stft_kernel_mag", st);
     if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);
@@ -987,7 +999,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         // decimation ladder (levels 1 .. n_levels-1), then one launch per distinct n_fft
         const int ntaps = (int)p.taps.size(), D = (ntaps - 1) / 2;
         const int dlen = dec_front_pad(D) + kDecTile + D + 8;
-        const int dplen = ((dlen + ((dlen >> 5) << 2)) + 7) & ~3;
+        const int dplen = ((dlen + ((dlen >> 4) << 2)) + 7) & ~3;
         const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
         for (int l = 1; l < p.n_levels; ++l) {
