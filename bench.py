@@ -362,8 +362,18 @@ def run_ours(args):
                                  'share_of_step': v['ms'] / ms_total,
                                  'algorithmic_GBps': bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
     top = max(kern.items(), key=lambda kv: kv[1]['ms_total'])
+    # measured DRAM traffic per launch of that kernel (ncu --set full capture of this workload, profiles/r01_traffic.json)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['traffic_bytes_per_launch']
+        ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256>(CqtParams)',
+                    'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
+        if B == default_batch:
+            traffic = tj.get(args.workload, {}).get(ncu_name)
+    except Exception:
+        pass
     roofline = {'kernel': top[0], 'bound': 'hbm', 'achieved': top[1]['algorithmic_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': (top[1]['algorithmic_GBps'] or 0.0) / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': (top[1]['algorithmic_GBps'] or 0.0) / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'note': 'FP32-SIMT/shared-memory bound kernel (SURVEY.md 8d): the HBM fraction is reported as required; '
                         'see DESIGN.md for the FP32 roofline', 'kernels': kern}
     step_bytes = sum(B * algorithmic_bytes(m, n) for m, n in zip(mods, n_per))
