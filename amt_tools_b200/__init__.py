@@ -11,6 +11,6 @@ Import patterns of the reference keep working with the package name swapped:
 from . import _lib  # noqa: F401  (fails loudly when libamtfeat.so has not been built)
 from . import features
 from .features import (FeatureCombo, FeatureModule, CQT, HCQT, HVQT, MelSpec, SignalPower, STFT, VQT,
-                       WaveformWrapper)
+                       WaveformWrapper, framify_activations)
 
 __version__ = '0.1.0'

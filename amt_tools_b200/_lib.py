@@ -59,6 +59,8 @@ def _load():
         'amtfeat_process': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, P, C.c_size_t, P]),
         'amtfeat_process_host': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, C.c_int64, C.c_int64, P, P, P,
                                            C.c_size_t, P]),
+        'amtfeat_framify_hops': (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
+        'amtfeat_framify': (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
         'amtfeat_profile_enable': (C.c_int, [P, C.c_int]),
         'amtfeat_profile_read': (C.c_int, [P, C.c_char_p, C.c_size_t]),
     }

@@ -165,6 +165,23 @@ int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const i
     return AMTFEAT_OK;
 }
 
+int64_t amtfeat_framify_hops(int64_t num_frames, int win_length, int hop_length, int pad) {
+    if (win_length <= 0 || hop_length <= 0 || num_frames < 0) return -1;
+    const int64_t pad_length = win_length / 2;
+    const int64_t padded = pad ? num_frames + 2 * pad_length : (num_frames > win_length ? num_frames : win_length);
+    return (padded - 2 * pad_length) / hop_length;   // tools/utils.py:2971
+}
+
+int amtfeat_framify(const float *d_in, int64_t rows, int64_t num_frames, int win_length, int hop_length, int pad, float *d_out,
+                    void *stream) {
+    const int64_t hops = amtfeat_framify_hops(num_frames, win_length, hop_length, pad);
+    if (hops < 0 || rows < 0) { amtfeat::set_error("invalid framify arguments"); return AMTFEAT_ERR_INVALID; }
+    const int64_t pad_length = win_length / 2;
+    const int64_t padded = pad ? num_frames + 2 * pad_length : (num_frames > win_length ? num_frames : win_length);
+    const int64_t lpad = (padded - num_frames) / 2;   // librosa.util.pad_center
+    return amtfeat::framify(d_in, rows, num_frames, win_length, hop_length, lpad, hops, d_out, stream);
+}
+
 int amtfeat_profile_enable(amtfeat_plan *plan, int enable) {
     if (!plan) return AMTFEAT_ERR_INVALID;
     plan->p.prof_enabled = enable != 0;

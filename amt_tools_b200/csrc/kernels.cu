@@ -297,6 +297,30 @@ __global__ void __launch_bounds__(kThreads) frames_kernel(const float *__restric
     out[cm.out_off + (long long)j * cm.T + t] = (g >= 0 && g < cm.n) ? __ldg(audio + cm.in_off + g) : 0.f;
 }
 
+// Device-side `tools.framify_activations` (amt_tools/tools/utils.py:2922-2984, used by TabCNN.pre_proc,
+// models/tabcnn.py:123-127): out[r][i][w] = padded[r][i * hop + w], zero padding of `lpad` frames on the left.
+__global__ void __launch_bounds__(kThreads) framify_kernel(const float *__restrict__ in, float *__restrict__ out, long long rows,
+                                                            long long T, int win, int hop, long long lpad, long long hops) {
+    const long long per_row = hops * win, total = rows * per_row;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const long long r = idx / per_row, rem = idx - r * per_row;
+        const long long i = rem / win;
+        const int w = (int)(rem - i * win);
+        const long long t = i * hop + w - lpad;
+        out[idx] = (t >= 0 && t < T) ? __ldg(in + r * T + t) : 0.f;
+    }
+}
+
+int framify(const float *d_in, long long rows, long long T, int win, int hop, long long lpad, long long hops, float *d_out,
+            void *stream) {
+    const long long total = rows * hops * win;
+    if (total <= 0) return AMTFEAT_OK;
+    const unsigned grid = (unsigned)std::min<long long>((total + kThreads - 1) / kThreads, 148 * 32);
+    framify_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_in, d_out, rows, T, win, hop, lpad, hops);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K6 : dB epilogue (common.py:199 + 224-225, mel.py:94, power.py:55)
 // ------------------------------------------------------------------------------------------------

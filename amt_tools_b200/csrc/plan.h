@@ -139,6 +139,8 @@ void free_plan_device(Plan &p);
 size_t workspace_bytes(const Plan &p, int batch, const int64_t *n);
 int launch_count(const Plan &p, int batch, const int64_t *n);
 int profile_read(const Plan &p, std::string &json);
+int framify(const float *d_in, long long rows, long long T, int win, int hop, long long lpad, long long hops, float *d_out,
+            void *stream);
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
             int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream);
 

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 
 __all__ = ['FeatureModule', 'WaveformWrapper', 'STFT', 'MelSpec', 'VQT', 'CQT', 'HVQT', 'HCQT', 'SignalPower',
-           'FeatureCombo']
+           'FeatureCombo', 'framify_activations']
 
 NOTE_C1_HZ = 440.0 * 2.0 ** ((24 - 69) / 12.0)  # librosa.note_to_hz('C1'), vqt.py:44
 
@@ -490,3 +490,23 @@ class FeatureCombo(FeatureModule):
 
     def get_feature_size(self):
         return NotImplementedError
+
+
+def framify_activations(activations, win_length, hop_length=1, pad=True):
+    """
+    Device-side `tools.framify_activations` (amt_tools/tools/utils.py:2922-2984): chunk a CUDA tensor (..., T) into
+    overlapping frames (..., num_hops, win_length) without leaving the device (TabCNN.pre_proc, models/tabcnn.py:123-127).
+    """
+    if not (isinstance(activations, torch.Tensor) and activations.is_cuda):
+        raise ValueError('framify_activations expects a CUDA tensor (there is no CPU compute path)')
+    x = activations.to(torch.float32).contiguous()
+    T = int(x.shape[-1])
+    rows = int(x.numel() // max(T, 1)) if T else int(np.prod(x.shape[:-1]))
+    hops = int(_lib.lib.amtfeat_framify_hops(T, int(win_length), int(hop_length), int(bool(pad))))
+    if hops < 0:
+        raise ValueError('invalid framify arguments')
+    with torch.cuda.device(x.device):
+        out = torch.empty(tuple(x.shape[:-1]) + (hops, int(win_length)), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib.amtfeat_framify(x.data_ptr(), rows, T, int(win_length), int(hop_length), int(bool(pad)),
+                                            out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream))
+    return out

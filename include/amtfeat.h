@@ -141,6 +141,15 @@ AMTFEAT_API int amtfeat_process_host(const amtfeat_plan *plan, const float *h_au
 AMTFEAT_API int amtfeat_launch_count(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
 
 /*
+ * Consumer-side helper: tools.framify_activations (amt_tools/tools/utils.py:2922-2984) on the device, so
+ * that TabCNN.pre_proc (models/tabcnn.py:123-127) needs no host round trip.  d_in is (rows, num_frames) row-major, d_out is
+ * (rows, hops, win_length) with hops = amtfeat_framify_hops(...); zero padding as librosa.util.pad_center.
+ */
+AMTFEAT_API int64_t amtfeat_framify_hops(int64_t num_frames, int win_length, int hop_length, int pad);
+AMTFEAT_API int amtfeat_framify(const float *d_in, int64_t rows, int64_t num_frames, int win_length, int hop_length, int pad,
+                                float *d_out, void *stream);
+
+/*
  * Measurement hook (no reference counterpart): when enabled, amtfeat_process records a CUDA event pair
  * around every kernel it launches on the launching stream; amtfeat_profile_read waits for them and
  * writes {"<kernel>": {"ms": total, "launches": n}, ...} as JSON, then clears the records.
