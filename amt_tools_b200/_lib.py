@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libamtfeat.so')
+LIB_PATH = os.environ.get('AMTFEAT_LIB') or os.path.join(_HERE, 'libamtfeat.so')   # env override: kernel A/B builds
 
 MAX_HARMONICS = 16
 (WAVEFORM, STFT, MEL, VQT, HVQT, POWER) = range(6)

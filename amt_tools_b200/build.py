@@ -28,12 +28,13 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """`out` / `defines` build an A/B variant (tools/variants.py) next to the product library."""
+    if out is None and not force and not needs_build():
         return LIB
     cmd = [_nvcc(), '-O3', '-std=c++17', '-lineinfo', '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden',
            '-gencode', 'arch=compute_100a,code=sm_100a', '-x', 'cu',
-           '-Xcompiler', '-DAMTFEAT_BUILD', '-o', LIB]
+           '-Xcompiler', '-DAMTFEAT_BUILD', '-o', out or LIB] + ['-D' + d for d in defines]
     if verbose:
         cmd += ['-Xptxas', '-v']
     cmd += [os.path.join(CSRC, f) for f in SOURCES]
@@ -43,7 +44,7 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed building libamtfeat.so')
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

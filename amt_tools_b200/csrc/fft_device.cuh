@@ -9,6 +9,13 @@
 
 #include <cuda_runtime.h>
 
+#ifndef AMT_FFT_PACKED
+#define AMT_FFT_PACKED 1
+#endif
+#ifndef AMT_TW_GLOBAL
+#define AMT_TW_GLOBAL 0
+#endif
+
 namespace amtfeat {
 
 template <int NC> struct FftCfg;
@@ -32,6 +39,34 @@ template <int NC> struct FftLayout {
     static constexpr int SCR = G * S;                // float2 per warp
     static constexpr int WARP_PITCH = 2 * SCR + 4;   // floats; +4 keeps rows of different warps on different banks
 };
+
+// Packed FP32x2 arithmetic (sm_100a FADD2 / FFMA2): one issue slot for both components of a complex value.  The FFT
+// kernels are issue-bound, not FMA-pipe-bound (profiles/), so halving the slots of the complex adds pays directly.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n sub.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd;}\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -76,8 +111,13 @@ template <int R> __device__ __forceinline__ void fft_regs(float2 (&v)[R]) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
                 const float2 a = v[blk + j], b = v[blk + j + half];
+#if AMT_FFT_PACKED
+                v[blk + j] = fadd2(a, b);
+                const float2 d = fsub2(a, b);
+#else
                 v[blk + j] = make_float2(a.x + b.x, a.y + b.y);
                 const float2 d = make_float2(a.x - b.x, a.y - b.y);
+#endif
                 const int m = j * (16 / half);  // twiddle exp(-2 pi i j / (2 half)) = w32(m)
                 if (m == 0) {
                     v[blk + j + half] = d;
@@ -97,7 +137,7 @@ template <int R> __device__ __forceinline__ void fft_regs(float2 (&v)[R]) {
 
 // Forward complex FFTs of one warp unit.  `load(g, n)` returns input point n of FFT g.
 // On return (after the trailing __syncwarp) scr[g * S + k] holds bin k of FFT g, k = 0..NC-1.
-template <int NC, typename LoadFn>
+template <int NC, bool TWG = false, typename LoadFn>
 __device__ __forceinline__ void warp_fft_unit(float2 *__restrict__ scr, const float2 *__restrict__ tw1, int lane, LoadFn load) {
     using L = FftLayout<NC>;
     constexpr int R1 = L::R1, R2 = L::R2, S = L::S;
@@ -114,7 +154,7 @@ __device__ __forceinline__ void warp_fft_unit(float2 *__restrict__ scr, const fl
 #pragma unroll
         for (int i = 0; i < R1; ++i) {
             const int k1 = brev<R1>(i);
-            const float2 y = (k1 == 0) ? v[i] : cmul(v[i], tw1[k1 * R2 + n2]);
+            const float2 y = (k1 == 0) ? v[i] : cmul(v[i], TWG ? __ldg(tw1 + k1 * R2 + n2) : tw1[k1 * R2 + n2]);
             scr[g * S + k1 * (R2 + 1) + n2] = y;
         }
     }

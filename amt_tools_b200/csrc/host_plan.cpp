@@ -10,6 +10,7 @@
 //   decimator     vqt.py:183   librosa.resample(res_type='soxr_hq')  Kaiser-windowed sinc, soxr HQ recipe
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 #include <cstdio>
 #include <cstring>
@@ -392,6 +393,29 @@ static int build_vqt(Plan &p) {
     }
     p.taps.resize(tapsd.size());
     for (size_t i = 0; i < tapsd.size(); ++i) p.taps[i] = (float)(tapsd[i] * std::sqrt(2.0));
+    // frequency response of the (float32) taps for the fast-convolution decimator: 2048-point blocks, every other
+    // output kept => the 2048-point spectrum folds onto 1024 points; a block yields 1024 - D outputs
+    p.decim_hh.clear();
+    {
+        const char *env = std::getenv("AMTFEAT_DECIM");
+        p.decim_direct = env && std::string(env) == "direct";
+        const int nt = (int)p.taps.size(), D = (nt - 1) / 2;
+        if (1024 - D >= 256) {
+            build_fft_tables(p, 2048);
+            std::vector<std::complex<double>> H(1025);
+            for (int k = 0; k <= 1024; ++k) {
+                std::complex<double> acc(0, 0);
+                for (int j = 0; j < nt; ++j) {
+                    const double ang = -2.0 * kPi * (double)((long long)j * k % 2048) / 2048.0;
+                    acc += (double)p.taps[j] * std::complex<double>(std::cos(ang), std::sin(ang));
+                }
+                H[k] = acc / 2048.0;   // 1/2 of the fold, 1/1024 of the inverse transform
+            }
+            p.decim_hh.resize(513);
+            for (int k = 0; k <= 512; ++k)
+                p.decim_hh[k] = cfloat4{(float)H[k].real(), (float)H[k].imag(), (float)H[1024 - k].real(), (float)-H[1024 - k].imag()};
+        }
+    }
 
     p.harm.clear();
     p.n_levels = 0;
@@ -515,33 +539,66 @@ static int build_vqt(Plan &p) {
         it.kmin = INT32_MAX;
         it.kmax = 0;
         const int NC = it.nfft / 2;
-        // group up to four adjacent rows of the same (harmonic, octave) run into blocks
+        // Rows of different harmonics that are the same wavelet (same band, same weights once the octave scale
+        // sqrt(sr / my_sr) and 1 / length are folded together) are projected once: `uniq` keeps the first
+        // occurrence and the list of (chan, bin) destinations it serves.
         const std::vector<CqtRow> &rs = g.second;
+        struct Uniq { size_t row; std::vector<std::pair<int, int>> dst; };
+        std::vector<Uniq> uniq;
+        for (size_t i = 0; i < rs.size(); ++i) {
+            int found = -1;
+            for (size_t u = 0; u < uniq.size() && found < 0; ++u) {
+                const CqtRow &a = rs[uniq[u].row], &b = rs[i];
+                if (a.chan == b.chan || a.col0 != b.col0 || a.cnt != b.cnt || (int)uniq[u].dst.size() >= kMaxDst) continue;
+                const double sa = std::sqrt((double)a.inv_len), sb = std::sqrt((double)b.inv_len);
+                bool same = true;
+                double ref = 0;
+                for (int q = 0; q < a.cnt; ++q) ref = std::max(ref, std::hypot((double)p.weights[a.woff + q].x, (double)p.weights[a.woff + q].y) * sa);
+                for (int q = 0; q < a.cnt && same; ++q) {
+                    const cfloat wa = p.weights[a.woff + q], wb = p.weights[b.woff + q];
+                    if (std::fabs(wa.x * sa - wb.x * sb) > 4e-7 * ref || std::fabs(wa.y * sa - wb.y * sb) > 4e-7 * ref) same = false;
+                    if ((wa.x == 0.f && wa.y == 0.f) != (wb.x == 0.f && wb.y == 0.f)) same = false;  // identical kept set
+                }
+                if (same) found = (int)u;
+            }
+            if (found >= 0) uniq[found].dst.push_back({rs[i].chan, rs[i].bin});
+            else uniq.push_back({i, {{rs[i].chan, rs[i].bin}}});
+        }
+        // group up to four adjacent unique rows (adjacent bins in every destination) into blocks
         it.blk0 = (int32_t)p.blocks.size();
-        for (size_t i = 0; i < rs.size();) {
+        auto adjacent = [&](const Uniq &a, const Uniq &b, int d) {
+            if (a.dst.size() != b.dst.size()) return false;
+            for (size_t k = 0; k < a.dst.size(); ++k)
+                if (b.dst[k].first != a.dst[k].first || b.dst[k].second != a.dst[k].second + d) return false;
+            return true;
+        };
+        for (size_t i = 0; i < uniq.size();) {
             size_t n = 1;
-            while (n < 4 && i + n < rs.size() && rs[i + n].chan == rs[i].chan && rs[i + n].bin == rs[i].bin + (int)n) ++n;
+            while (n < 4 && i + n < uniq.size() && adjacent(uniq[i], uniq[i + n], (int)n)) ++n;
             CqtBlock4 bl{};
             int lo = INT32_MAX, hi = 0;
             for (size_t r = 0; r < n; ++r) {
-                lo = std::min(lo, rs[i + r].col0);
-                hi = std::max(hi, rs[i + r].col0 + rs[i + r].cnt);
+                const CqtRow &rw = rs[uniq[i + r].row];
+                lo = std::min(lo, rw.col0);
+                hi = std::max(hi, rw.col0 + rw.cnt);
             }
             hi = std::min(hi, NC + 1);
             bl.col0 = lo;
             bl.steps = hi - lo;
             bl.woff = (int32_t)p.weights4.size();
-            bl.chan = rs[i].chan;
-            for (int r = 0; r < 4; ++r) {
-                bl.off[r] = r < (int)n ? rs[i + r].chan * p.F + rs[i + r].bin : -1;
-                bl.inv[r] = r < (int)n ? rs[i + r].inv_len : 0.f;
+            bl.ndst = (int32_t)uniq[i].dst.size();
+            for (int d = 0; d < kMaxDst; ++d) {
+                bl.chan[d] = d < bl.ndst ? uniq[i].dst[d].first : 0;
+                for (int r = 0; r < 4; ++r)
+                    bl.off[d][r] = (d < bl.ndst && r < (int)n) ? uniq[i + r].dst[d].first * p.F + uniq[i + r].dst[d].second : -1;
             }
+            for (int r = 0; r < 4; ++r) bl.inv[r] = r < (int)n ? rs[uniq[i + r].row].inv_len : 0.f;
             p.weights4.resize(p.weights4.size() + (size_t)bl.steps * 2, cfloat4{0, 0, 0, 0});
             for (int st = 0; st < bl.steps; ++st) {
                 const int col = lo + st;
                 float w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 for (size_t r = 0; r < n; ++r) {
-                    const CqtRow &rw = rs[i + r];
+                    const CqtRow &rw = rs[uniq[i + r].row];
                     if (col >= rw.col0 && col < rw.col0 + rw.cnt) {
                         const cfloat v = p.weights[rw.woff + (col - rw.col0)];
                         w[2 * r] = v.x;
@@ -557,6 +614,7 @@ static int build_vqt(Plan &p) {
             i += n;
         }
         it.nblk = (int32_t)p.blocks.size() - it.blk0;
+        it.nuniq = (int32_t)uniq.size();
         it.woff0 = it.nblk ? p.blocks[it.blk0].woff : 0;
         it.wcount = (int32_t)p.weights4.size() - it.woff0;
         int ktrue = 0;
@@ -620,7 +678,7 @@ std::string describe(const Plan &p) {
     o << "{\"kind\": " << c.kind << ", \"channels\": " << p.C << ", \"feature_size\": " << p.F << ", \"device\": " << p.device;
     if (c.kind == AMTFEAT_MEL) o << ", \"mel_nnz\": " << p.mel_w.size();
     if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
-        o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size()
+        o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size() << ", \"decimator\": \"" << ((p.decim_hh.empty() || p.decim_direct) ? "direct" : "fft") << "\""
           << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_nnz\": " << p.weights4.size() * 2 << ", \"eds_ref\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_ref;
         o << "], \"eds_lib\": [";
@@ -629,7 +687,7 @@ std::string describe(const Plan &p) {
         for (size_t i = 0; i < p.items.size(); ++i) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
-              << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
+              << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"unique_rows\": " << it.nuniq << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
         }
         o << "]";
     }

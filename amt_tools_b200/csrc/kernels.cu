@@ -449,6 +449,122 @@ __global__ void __launch_bounds__(kThreads) decimate_kernel(const float *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4 (fast form) : the same 2:1 decimator as overlap-save fast convolution.
+//   A block is 2048 input samples u[n] = x[2 m0 - D + n]; its circular convolution with the taps is exact for
+//   n >= 2 D, and keeping every other sample folds the 2048-point spectrum C = U H onto 1024 points:
+//   Cd[k] = (C[k] + conj(C[1024 - k])) / 2, y[m0 + j - D] = irfft_1024(Cd)[j], j = D .. 1023  (1024 - D outputs).
+//   One warp takes TWO blocks: forward real FFT of each (one 1024-point complex warp unit + split, fused with the
+//   multiplication by H and the fold), then ONE 1024-point complex transform inverts both at once
+//   (S = CdA + i CdB with Hermitian extension; IDFT(S) = conj(DFT(conj S)) = ydA + i ydB).
+//   ~100 flop per output sample instead of 2 * 389 for the direct form.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kDfWarps = 6, kDfThreads = kDfWarps * 32;
+constexpr int kDfCd = 520;   // float2 per warp for the folded spectrum of the first block (513 used)
+
+struct DecFftParams {
+    const float *audio;
+    float *ladder;
+    const ClipMeta *meta;
+    const float2 *tw1, *tw2;
+    const float4 *hh;
+    int level_out, D, M;
+};
+
+// Folded, filtered spectrum of the block whose packed complex FFT sits in scr: Cd[k], k = lane + 32 j.
+__device__ __forceinline__ void dec_fold(const float2 *scr, const DecFftParams &p, int lane, float2 (&cd)[17]) {
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+        const int k = lane + 32 * j;
+        if (k <= 512) {
+            const float2 A = scr[k], B = scr[(1024 - k) & 1023];
+            float2 E, T;
+            rfft_split(A, B, __ldg(p.tw2 + k), E, T);
+            const float4 h = __ldg(p.hh + k);
+            const float2 up = make_float2(E.x + T.x, E.y + T.y), um = make_float2(E.x - T.x, E.y - T.y);
+            const float2 c0 = cmul(make_float2(h.x, h.y), up), c1 = cmul(make_float2(h.z, h.w), um);
+            cd[j] = make_float2(c0.x + c1.x, c0.y + c1.y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFftParams p) {
+    using L = FftLayout<1024>;
+    constexpr int WP2 = L::WARP_PITCH / 2;
+    extern __shared__ __align__(16) float smem[];
+    float2 *s_tw1 = reinterpret_cast<float2 *>(smem);      // 1024
+    float2 *s_scr = s_tw1 + 1024;                          // kDfWarps * WP2
+    float2 *s_cd = s_scr + kDfWarps * WP2;                 // kDfWarps * kDfCd
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int len_out = cm->lvl_len[p.level_out], len_in = cm->lvl_len[p.level_out - 1];
+    if ((long long)blockIdx.x * kDfWarps * 2 * p.M >= len_out) return;
+    for (int i = tid; i < 1024; i += kDfThreads) s_tw1[i] = p.tw1[i];
+    __syncthreads();
+    const long long mA = ((long long)blockIdx.x * kDfWarps + warp) * 2 * p.M, mB = mA + p.M;
+    if (mA >= len_out) return;
+    const float *src = (p.level_out == 1 ? p.audio : p.ladder) + cm->lvl_off[p.level_out - 1];
+    float *dst = p.ladder + cm->lvl_off[p.level_out];
+    float2 *scr = s_scr + warp * WP2, *cdA = s_cd + warp * kDfCd;
+
+    auto forward = [&](long long m0) {
+        const long long base = 2 * m0 - p.D;               // even: D is even
+        const bool interior = base >= 0 && base + 2048 <= len_in;
+        warp_fft_unit<1024>(scr, s_tw1, lane, [&](int, int n) {
+            const long long i = base + 2 * n;
+            if (interior) return __ldg(reinterpret_cast<const float2 *>(src + i));
+            float2 v;
+            v.x = (i >= 0 && i < len_in) ? __ldg(src + i) : 0.f;
+            v.y = (i + 1 >= 0 && i + 1 < len_in) ? __ldg(src + i + 1) : 0.f;
+            return v;
+        });
+    };
+
+    float2 cd[17];
+    forward(mA);
+    dec_fold(scr, p, lane, cd);
+#pragma unroll
+    for (int j = 0; j < 17; ++j)
+        if (lane + 32 * j <= 512) cdA[lane + 32 * j] = cd[j];
+    __syncwarp();
+    const bool haveB = mB < len_out;
+    if (haveB) {
+        forward(mB);
+        dec_fold(scr, p, lane, cd);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 17; ++j) cd[j] = make_float2(0.f, 0.f);
+    }
+    __syncwarp();
+    // conj(S) in the padded [n1][n2] layout the transform's first pass reads and overwrites in place
+#pragma unroll
+    for (int j = 0; j < 17; ++j) {
+        const int k = lane + 32 * j;
+        if (k <= 512) {
+            const float2 a = cdA[k], b = cd[j];
+            scr[(k >> 5) * 33 + (k & 31)] = make_float2(a.x - b.y, -a.y - b.x);
+            if (k >= 1 && k <= 511) {
+                const int n = 1024 - k;
+                scr[(n >> 5) * 33 + (n & 31)] = make_float2(a.x + b.y, a.y - b.x);
+            }
+        }
+    }
+    __syncwarp();
+    warp_fft_unit<1024>(scr, s_tw1, lane, [&](int, int n) { return scr[(n >> 5) * 33 + (n & 31)]; });
+    // scr[n] = conj(ydA[n] + i ydB[n])
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const int n = lane + 32 * j;
+        if (n >= p.D) {
+            const float2 r = scr[n];
+            const long long ma = mA + n - p.D, mb = mB + n - p.D;
+            if (ma < len_out) dst[ma] = r.x;
+            if (haveB && mb < len_out) dst[mb] = -r.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 + K5 : CQT / VQT / HCQT response of one (ladder level, n_fft) item
 // ------------------------------------------------------------------------------------------------
 
@@ -463,7 +579,7 @@ struct CqtParams {
     const CqtRow *rows;
     const float2 *weights;
     const float2 *tw1, *tw2;
-    int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off;
+    int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off, blk_off;
 };
 
 // Shared prologue of both CQT kernels: stage the level signal, run the warp FFT unit.
@@ -473,20 +589,23 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
     using L = FftLayout<NC>;
     constexpr int G = L::G, TT = kWarpsPerCta * G, NFFT = 2 * NC, WP2 = L::WARP_PITCH / 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if !AMT_TW_GLOBAL
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i <= NC; i += kThreads) s_tw2[i] = p.tw2[i];
+#endif
     const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
     int shift, fstride;
     load_tile(s_tile, src, cm->lvl_len[it.level], (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
     __syncthreads();
     float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
     const bool vec_ok = ((shift | fstride) & 1) == 0;
+    const float2 *tw1 = AMT_TW_GLOBAL ? p.tw1 : s_tw1;
     if (vec_ok) {
-        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+        warp_fft_unit<NC, AMT_TW_GLOBAL != 0>(scr, tw1, lane, [&](int g, int n) {
             return *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
         });
     } else {
-        warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+        warp_fft_unit<NC, AMT_TW_GLOBAL != 0>(scr, tw1, lane, [&](int g, int n) {
             const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
             return make_float2(x[0], x[1]);
         });
@@ -529,6 +648,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     int *s_rowoff = reinterpret_cast<int *>(s_stage + p.stage_blocks * 4 * (TT + 1));
     float2 *Dbuf = reinterpret_cast<float2 *>(s_scr + p.dbuf_off);
     float4 *s_w = reinterpret_cast<float4 *>(s_scr + p.w_off);
+    const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_scr + p.blk_off);   // the item's block descriptors
     {   // real-FFT split on the band, held in registers across the barrier that retires the scratch and the audio tile
         const float2 *scr = reinterpret_cast<const float2 *>(s_scr) + warp * WP2;
         const int kb = it.kmax - it.kmin + 1;
@@ -543,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                     const int k = it.kmin + kk;
                     const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
                     float2 E, Tw;
-                    rfft_split(A, B, s_tw2[k], E, Tw);
+                    rfft_split(A, B, AMT_TW_GLOBAL ? __ldg(p.tw2 + k) : s_tw2[k], E, Tw);
                     X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
                 }
             }
@@ -554,6 +674,14 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
             for (int i = tid; i < it.wcount; i += kThreads) {
                 const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_w + i));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + i) : "memory");
+            }
+            {   // ... and its block descriptors (112 B each, 16-byte granules)
+                const float4 *bsrc = reinterpret_cast<const float4 *>(p.blocks + it.blk0);
+                const int n16 = it.nblk * (int)(sizeof(CqtBlock4) / 16);
+                for (int i = tid; i < n16; i += kThreads) {
+                    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<const float4 *>(s_blk) + i));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(bsrc + i) : "memory");
+                }
             }
             asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
@@ -573,10 +701,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
     for (int b0 = 0; b0 < it.nblk; b0 += p.stage_blocks) {
         const int nb = min(p.stage_blocks, it.nblk - b0);
-        for (int rs = tid; rs < nb * 4; rs += kThreads) s_rowoff[rs] = p.blocks[it.blk0 + b0 + (rs >> 2)].off[rs & 3];
+        for (int rs = tid; rs < nb * 4 * kMaxDst; rs += kThreads) {   // s_rowoff[(block row)][destination]
+            const int d = rs % kMaxDst, br = rs / kMaxDst;
+            s_rowoff[rs] = s_blk[b0 + (br >> 2)].off[d][br & 3];
+        }
         for (int w = sub; w < nb * NCHUNK; w += NSUB) {
             const int bi = w / NCHUNK, ch = w % NCHUNK;
-            const CqtBlock4 *bl = p.blocks + it.blk0 + b0 + bi;
+            const CqtBlock4 *bl = s_blk + b0 + bi;
             const int steps = bl->steps;
             const float4 *wt = s_w + (bl->woff - it.woff0);
             const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
@@ -604,14 +735,27 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 float vmax = (t0 + t < T) ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
 #pragma unroll
                 for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                if (lt == 0) atomicMax(&s_max[bl->chan], __float_as_int(vmax));
+                if (lt == 0)
+                    for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
             }
         }
         __syncthreads();
         for (int idx = tid; idx < nb * 4 * TT; idx += kThreads) {
             const int t = idx % TT, rs = idx / TT;
-            const int off = s_rowoff[rs];
-            if (off >= 0 && t0 + t < T) out[(long long)off * T + t0 + t] = s_stage[rs * (TT + 1) + t];
+            if (t0 + t < T) {
+                const float v = s_stage[rs * (TT + 1) + t];
+                // rows shared by several harmonics are stored to each of them (the list is -1 terminated)
+                int off = s_rowoff[rs * kMaxDst];
+                if (off >= 0) {
+                    out[(long long)off * T + t0 + t] = v;
+#pragma unroll
+                    for (int d = 1; d < kMaxDst; ++d) {
+                        off = s_rowoff[rs * kMaxDst + d];
+                        if (off < 0) break;
+                        out[(long long)off * T + t0 + t] = v;
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -654,7 +798,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
                 const int g = q / kb, k = it.kmin + (q - g * kb);
                 const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
                 float2 E, Tw;
-                rfft_split(A, B, s_tw2[k], E, Tw);
+                rfft_split(A, B, AMT_TW_GLOBAL ? __ldg(p.tw2 + k) : s_tw2[k], E, Tw);
                 X[j] = make_float2(E.x + Tw.x, E.y + Tw.y);
             }
         }
@@ -767,12 +911,14 @@ int upload_plan(Plan &p) {
         (rc = set_attrs<4>()))
         return rc;
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
     if ((rc = upload_vec(p, p.mel_cnt, &p.d_mel_cnt))) return rc;
     if ((rc = upload_vec(p, p.mel_off, &p.d_mel_off))) return rc;
     if ((rc = upload_vec(p, p.mel_w, &p.d_mel_w))) return rc;
     if ((rc = upload_vec(p, p.taps, &p.d_taps))) return rc;
+    if ((rc = upload_vec(p, p.decim_hh, &p.d_decim_hh))) return rc;
     if ((rc = upload_vec(p, p.rows, &p.d_rows))) return rc;
     if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
     if ((rc = upload_vec(p, p.blocks, &p.d_blocks))) return rc;
@@ -931,11 +1077,12 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
         for (int i = item0; i < item0 + nitems; ++i) maxw = std::max(maxw, p.items[i].wcount);
         cp.stage_blocks = std::max(1, std::min(maxblk, 4096 / (4 * (TT + 1))));
         cp.stage_rows = 0;
-        const int stage_floats = (cp.stage_blocks * 4 * (TT + 2) + 3) / 4 * 4;
+        const int stage_floats = (cp.stage_blocks * 4 * (TT + 1 + kMaxDst) + 3) / 4 * 4;
         const int dbuf_floats = (maxkb * (TT + 1) * 2 + 3) / 4 * 4;
         cp.dbuf_off = stage_floats;
         cp.w_off = stage_floats + dbuf_floats;
-        const int need = cp.w_off + maxw * 4;
+        cp.blk_off = cp.w_off + maxw * 4;
+        const int need = cp.blk_off + maxblk * (int)(sizeof(CqtBlock4) / 4);
         cp.tile_floats = std::max(cp.tile_floats, (need - scratch_floats + 3) / 4 * 4);
         smem = (size_t)(2 * NC + 2 * (NC + 2) + scratch_floats + cp.tile_floats) * sizeof(float);
     } else {
@@ -1026,11 +1173,25 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         const int dplen = ((dlen + ((dlen >> 4) << 2)) + 7) & ~3;
         const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
+        const bool fast = !p.decim_hh.empty() && !p.decim_direct;
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
-            dim3 grid((unsigned)((len + kDecTile - 1) / kDecTile), batch);
-            ProfScope ps(p, "decimate_kernel", st);
-            decimate_kernel<<<grid, kThreads, dsmem, st>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
+            if (fast) {
+                using L = FftLayout<1024>;
+                DecFftParams dp{};
+                dp.audio = d_audio; dp.ladder = d_ladder; dp.meta = d_meta; dp.hh = reinterpret_cast<const float4 *>(p.d_decim_hh);
+                const FftTables &ft = p.fft.at(1024);
+                dp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1); dp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
+                dp.level_out = l; dp.D = D; dp.M = 1024 - D;
+                const size_t fsmem = (size_t)(1024 + kDfWarps * (L::WARP_PITCH / 2) + kDfWarps * kDfCd) * sizeof(float2);
+                dim3 grid((unsigned)((len + (int64_t)kDfWarps * 2 * dp.M - 1) / ((int64_t)kDfWarps * 2 * dp.M)), batch);
+                ProfScope ps(p, "decimate_fft_kernel", st);
+                decimate_fft_kernel<<<grid, kDfThreads, fsmem, st>>>(dp);
+            } else {
+                dim3 grid((unsigned)((len + kDecTile - 1) / kDecTile), batch);
+                ProfScope ps(p, "decimate_kernel", st);
+                decimate_kernel<<<grid, kThreads, dsmem, st>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
+            }
             AMT_CUDA(cudaGetLastError());
         }
         CqtParams cp{};

@@ -43,20 +43,29 @@ struct CqtRow {
 // Up to four adjacent rows of one (harmonic, octave) run, projected together by the lanes that share a
 // frame: every FFT bin fetched from shared memory feeds four complex MACs, and the block's weights are a
 // warp-uniform stream of [step][4 rows] complex values (two 16-byte loads per step).
+//
+// Harmonics whose frequencies are an octave apart (h = 0.5, 1, 2 of an HCQT) meet on the same ladder level with
+// the same normalised frequencies, i.e. the same wavelet rows: such rows are projected ONCE and stored to every
+// destination channel (`ndst` > 1).
+constexpr int kMaxDst = 4;
 struct CqtBlock4 {
     int32_t col0;       // first FFT bin of the union band of the rows
     int32_t steps;      // width of the union band (weights outside a row's own band are stored as zeros)
     int32_t woff;       // offset into weights4, in float4 (2 float4 per step)
-    int32_t chan;       // output channel (harmonic index) of all rows of the block
-    int32_t off[4];     // chan * F + bin of each row, -1 if absent
+    int32_t ndst;       // number of destination channels sharing these rows
+    int32_t chan[kMaxDst];      // output channel (harmonic index) of each destination
+    int32_t off[kMaxDst][4];    // chan * F + bin of each row per destination, -1 if absent
     float inv[4];       // 1 / length of each row (applied to the power)
 };
+
+static_assert(sizeof(CqtBlock4) % 16 == 0, "block descriptors are staged into shared memory in 16-byte granules");
 
 // All rows that consume the FFT frames of one (ladder level, n_fft) pair.
 struct CqtItem {
     int32_t level, nfft, hop, blk0, nblk, kmin, kmax, nrows;
     int32_t row0, kmax_true;    // per-row tables (small-n_fft fallback kernel); last bin with a non-zero weight
     int32_t woff0, wcount;      // the item's slice of weights4 (float4 units), staged into shared memory per CTA
+    int32_t nuniq, pad_;        // distinct rows after merging rows shared by several harmonics
 };
 
 struct cfloat4 {
@@ -90,6 +99,11 @@ struct Plan {
     int n_oct = 0, n_filters = 0, n_levels = 0;
     std::vector<HarmonicInfo> harm;
     std::vector<float> taps;                   // 2:1 decimator, includes the sqrt(2) of `scale=True`
+    // Fast-convolution form of the same decimator (decimate_fft_kernel): per bin k = 0..512 of the folded
+    // (decimated) 1024-point spectrum, (Ha, Hb) = (H[k], conj(H[1024 - k])) / 2048 with H the 2048-point DFT of the
+    // float32 taps.  Empty when the taps are too long for a 2048-point block (the direct kernel is used then).
+    std::vector<cfloat4> decim_hh;
+    bool decim_direct = false;                 // AMTFEAT_DECIM=direct forces the direct-form kernel (tests / A-B)
     std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
     std::vector<cfloat> weights;               // per-row weights (host only)
     std::vector<CqtBlock4> blocks;
@@ -106,6 +120,7 @@ struct Plan {
 
     // device copies
     float *d_window = nullptr, *d_mel_w = nullptr, *d_taps = nullptr;
+    cfloat4 *d_decim_hh = nullptr;
     int32_t *d_mel_start = nullptr, *d_mel_cnt = nullptr, *d_mel_off = nullptr;
     CqtRow *d_rows = nullptr;
     cfloat *d_weights = nullptr;

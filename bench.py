@@ -198,7 +198,7 @@ def kernel_algorithmic_bytes(mod, name, n):
             if it['n_fft'] == nfft:
                 total += 4 * int(np.ceil(n / 2.0 ** it['level'])) + 4 * it['rows'] * T
         return total
-    if name == 'decimate_kernel':
+    if name in ('decimate_kernel', 'decimate_fft_kernel'):
         return sum(4 * int(np.ceil(n / 2.0 ** (l - 1))) + 4 * int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
     if name == 'db_epilogue_kernel':
         return 8 * mod.get_num_channels() * mod.get_feature_size() * T
@@ -356,7 +356,7 @@ def run_ours(args):
         n = n_per[mods.index(m)]
         per_launch_ms = v['ms'] / max(v['launches'], 1)
         bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n)
-        if k == 'decimate_kernel':  # one launch per ladder level: average over the levels
+        if k in ('decimate_kernel', 'decimate_fft_kernel'):  # one launch per ladder level: average over the levels
             bytes_per_launch = bytes_per_launch / max(1, m.describe()['n_levels'] - 1)
         kern[mname + '.' + k] = {'ms_total': v['ms'], 'launches': v['launches'], 'avg_ms': per_launch_ms,
                                  'share_of_step': v['ms'] / ms_total,

@@ -253,3 +253,21 @@ def test_full_size_properties():
     want = ((fr * w) ** 2).sum(1)
     got = energy[(2048 + np.arange(100) * 2048 + 1024) // 512]
     assert torch.allclose(got.cpu(), want, rtol=1e-5)
+
+
+def test_fast_convolution_decimator_matches_direct_form(monkeypatch):
+    # K4 has two forms: decimate_fft_kernel (overlap-save, default) and decimate_kernel (direct polyphase FIR,
+    # AMTFEAT_DECIM=direct).  Same taps, same ladder: the deepest levels must agree to float32 rounding.
+    y = piano_like(22050 * 7 + 123, 22050, seed=81)
+    kw = dict(sample_rate=22050, hop_length=256, decibels=False, n_bins=360, bins_per_octave=60)
+    fast = ab.HCQT(**kw)
+    assert fast.describe()['decimator'] == 'fft'
+    a = fast.process_audio([y, y[:30011]])
+    monkeypatch.setenv('AMTFEAT_DECIM', 'direct')
+    direct = ab.HCQT(**kw)
+    assert direct.describe()['decimator'] == 'direct'
+    b = direct.process_audio([y, y[:30011]])
+    for u, v in zip(a, b):
+        assert rel_l2(u.cpu().numpy(), v.cpu().numpy()) < 2e-6
+        # lowest octave: 7 cascaded float32 stages; each form is ~5e-6 from the float64 oracle there (tools/dbg_decim.py)
+        assert rel_l2(u[0, :60].cpu().numpy(), v[0, :60].cpu().numpy()) < 3e-5
