@@ -77,6 +77,25 @@ __device__ __forceinline__ void load_tile(float *tile, const float *__restrict__
     }
 }
 
+// Asynchronous form of load_tile for overlapping frames (hop <= nfft): 16-byte cp.async with zero fill outside [0, n)
+// (the tile start is 4-element aligned relative to the clip, so a vector is either wholly before the clip or has a
+// valid prefix).  The caller commits / waits the group.
+__device__ __forceinline__ void load_tile_async(float *tile, const float *__restrict__ src, long long n, long long s0, int hop,
+                                                int nfft, int TT, int tid, int &shift) {
+    shift = (int)(((s0 % 4) + 4) % 4);
+    const long long a0 = s0 - shift;
+    const int span = (TT - 1) * hop + nfft + shift;
+    const int nvec = (span + 3) >> 2;
+    for (int i = tid; i < nvec; i += kThreads) {
+        const long long g = a0 + 4ll * i;
+        int valid = 0;
+        if (g >= 0 && g < n) valid = (int)(n - g < 4 ? n - g : 4) * 4;
+        const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(tile + 4 * i));
+        const float *gp = src + (valid ? g : 0);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(valid) : "memory");
+    }
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -96,7 +115,7 @@ struct StftParams {
     const float2 *tw1, *tw2;
     const int *mel_seg_start, *mel_gsteps, *mel_goff;
     const float2 *mel_ww;
-    int hop, pad, n_mels, decibels, tile_floats, scr_floats;
+    int hop, pad, n_mels, decibels, tile_floats, scr_floats, tiles_per_cta;
 };
 
 constexpr int MODE_STFT = 0, MODE_MEL = 1;
@@ -127,123 +146,146 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
     const int T = cm->T;
-    const int t0 = blockIdx.x * TT;
-    if (t0 >= T) return;
+    // A CTA walks `tiles_per_cta` consecutive tiles of one clip: the twiddles are staged once, and the audio of the
+    // next tile streams into shared memory (cp.async) while the current tile is projected and stored.
+    const int ntiles = (T + TT - 1) / TT;
+    const int tile_begin = blockIdx.x * p.tiles_per_cta;
+    if (tile_begin >= ntiles) return;
+    const int tile_end = min(ntiles, tile_begin + p.tiles_per_cta);
+    const float *src = p.audio + cm->in_off;
+    const bool overlap = p.hop <= NFFT;
+    float *out = p.out + cm->out_off;
+    float vmax = 0.f;
 
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i < NC / 2; i += kThreads) s_tw2[i] = p.tw2[i];
-    int shift, fstride;
-    load_tile(s_tile, p.audio + cm->in_off, cm->n, (long long)t0 * p.hop - p.pad, p.hop, NFFT, TT, tid, shift, fstride);
-    __syncthreads();
+    int shift = 0, fstride = overlap ? p.hop : NFFT;
+    if (overlap) {
+        load_tile_async(s_tile, src, cm->n, (long long)tile_begin * TT * p.hop - p.pad, p.hop, NFFT, TT, tid, shift);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
 
-    float2 *scr = reinterpret_cast<float2 *>(s_scr + warp * L::WARP_PITCH);
-    {
-        const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
-        const bool vec_ok = ((shift | fstride) & 1) == 0;
-        if (vec_ok) {
-            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
-                const float2 x = *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
-                const float2 w = __ldg(win2 + n);
-                return make_float2(x.x * w.x, x.y * w.y);
-            });
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int t0 = tile * TT;
+        if (overlap) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         } else {
-            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
-                const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
-                const float2 w = __ldg(win2 + n);
-                return make_float2(x[0] * w.x, x[1] * w.y);
-            });
+            __syncthreads();   // previous iteration's readers of the scratch region are done
+            load_tile(s_tile, src, cm->n, (long long)t0 * p.hop - p.pad, p.hop, NFFT, TT, tid, shift, fstride);
         }
-    }
+        __syncthreads();       // tile (and, first time, the twiddles) visible; previous iteration's staging retired
 
-    // real-FFT split -> power spectrum in registers; after the barrier (scratch retired) it is written TRANSPOSED as
-    // Pbuf[k][frame] (frame fastest, odd pitch) so both the store below and the consumers are conflict free
-    float *Pbuf = s_scr;
-    {
-        float pw[16][2];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int q = lane + 32 * j;
-            const int g = q / (NC / 2), k = q % (NC / 2);
-            const float2 A = scr[g * S + k], B = scr[g * S + ((NC - k) & (NC - 1))];
-            float2 E, Tw;
-            rfft_split(A, B, s_tw2[k], E, Tw);
-            const float ax = E.x + Tw.x, ay = E.y + Tw.y, bx = E.x - Tw.x, by = E.y - Tw.y;
-            pw[j][0] = fmaf(ax, ax, ay * ay);
-            pw[j][1] = fmaf(bx, bx, by * by);
+        float2 *scr = reinterpret_cast<float2 *>(s_scr + warp * L::WARP_PITCH);
+        {
+            const float2 *win2 = reinterpret_cast<const float2 *>(p.window);
+            const bool vec_ok = ((shift | fstride) & 1) == 0;
+            if (vec_ok) {
+                warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                    const float2 x = *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+                    const float2 w = __ldg(win2 + n);
+                    return make_float2(x.x * w.x, x.y * w.y);
+                });
+            } else {
+                warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                    const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
+                    const float2 w = __ldg(win2 + n);
+                    return make_float2(x[0] * w.x, x[1] * w.y);
+                });
+            }
         }
-        float pmid = 0.f;
-        if (lane < G) {
-            const float2 A = scr[lane * S + NC / 2];
-            pmid = fmaf(A.x, A.x, A.y * A.y);
+
+        // real-FFT split -> power spectrum in registers; after the barrier (scratch retired) it is written TRANSPOSED as
+        // Pbuf[k][frame] (frame fastest, odd pitch) so both the store below and the consumers are conflict free
+        float *Pbuf = s_scr;
+        {
+            float pw[16][2];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int q = lane + 32 * j;
+                const int g = q / (NC / 2), k = q % (NC / 2);
+                const float2 A = scr[g * S + k], B = scr[g * S + ((NC - k) & (NC - 1))];
+                float2 E, Tw;
+                rfft_split(A, B, s_tw2[k], E, Tw);
+                const float ax = E.x + Tw.x, ay = E.y + Tw.y, bx = E.x - Tw.x, by = E.y - Tw.y;
+                pw[j][0] = fmaf(ax, ax, ay * ay);
+                pw[j][1] = fmaf(bx, bx, by * by);
+            }
+            float pmid = 0.f;
+            if (lane < G) {
+                const float2 A = scr[lane * S + NC / 2];
+                pmid = fmaf(A.x, A.x, A.y * A.y);
+            }
+            __syncthreads();   // every warp is done with the audio tile and its FFT scratch
+            if (overlap && tile + 1 < tile_end) {
+                load_tile_async(s_tile, src, cm->n, (long long)(t0 + TT) * p.hop - p.pad, p.hop, NFFT, TT, tid, shift);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int q = lane + 32 * j;
+                const int g = q / (NC / 2), k = q % (NC / 2);
+                Pbuf[k * PT + warp * G + g] = pw[j][0];
+                Pbuf[(NC - k) * PT + warp * G + g] = pw[j][1];
+            }
+            if (lane < G) Pbuf[(NC / 2) * PT + warp * G + lane] = pmid;
         }
         __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int q = lane + 32 * j;
-            const int g = q / (NC / 2), k = q % (NC / 2);
-            Pbuf[k * PT + warp * G + g] = pw[j][0];
-            Pbuf[(NC - k) * PT + warp * G + g] = pw[j][1];
-        }
-        if (lane < G) Pbuf[(NC / 2) * PT + warp * G + lane] = pmid;
-    }
-    __syncthreads();
 
-    float vmax = 0.f;
-    float *out = p.out + cm->out_off;
-    if (MODE == MODE_MEL) {
-        // Sparse mel projection, segment form: FFT bin k lies between two mel centres and feeds exactly the rising slope
-        // of filter seg(k) and the falling slope of filter seg(k) - 1, so every power value is read once:
-        //   U[s] = sum_{k in segment s} up_k P[k],  V[s] = sum down_k P[k],  mel[m] = U[m] + V[m + 1].
-        // One thread per (segment, chunk of 8 frames); the (up, down) weights are padded lane-major per group of 32 segments.
-        float *s_U = Pbuf + (NC + 1) * PT, *s_V = s_U + (p.n_mels + 1) * PT;
-        const int nseg = p.n_mels + 1, ngroups = (nseg + 31) >> 5;
-        constexpr int NCHUNK = TT / 8;
-        for (int w = warp; w < ngroups * NCHUNK; w += kWarpsPerCta) {
-            const int grp = w / NCHUNK, ch = w % NCHUNK;
-            const int sgm = grp * 32 + lane;
-            const int steps = __ldg(p.mel_gsteps + grp);
-            const float2 *ww = p.mel_ww + __ldg(p.mel_goff + grp) + lane;
-            const int k0 = sgm < nseg ? __ldg(p.mel_seg_start + sgm) : 0;
-            float u[8], v[8];
+        if (MODE == MODE_MEL) {
+            // Sparse mel projection, segment form: FFT bin k lies between two mel centres and feeds exactly the rising slope
+            // of filter seg(k) and the falling slope of filter seg(k) - 1, so every power value is read once:
+            //   U[s] = sum_{k in segment s} up_k P[k],  V[s] = sum down_k P[k],  mel[m] = U[m] + V[m + 1].
+            // One thread per (segment, chunk of 8 frames); the (up, down) weights are padded lane-major per group of 32 segments.
+            float *s_U = Pbuf + (NC + 1) * PT, *s_V = s_U + (p.n_mels + 1) * PT;
+            const int nseg = p.n_mels + 1, ngroups = (nseg + 31) >> 5;
+            constexpr int NCHUNK = TT / 8;
+            for (int w = warp; w < ngroups * NCHUNK; w += kWarpsPerCta) {
+                const int grp = w / NCHUNK, ch = w % NCHUNK;
+                const int sgm = grp * 32 + lane;
+                const int steps = __ldg(p.mel_gsteps + grp);
+                const float2 *ww = p.mel_ww + __ldg(p.mel_goff + grp) + lane;
+                const int k0 = sgm < nseg ? __ldg(p.mel_seg_start + sgm) : 0;
+                float u[8], v[8];
 #pragma unroll
-            for (int f = 0; f < 8; ++f) u[f] = v[f] = 0.f;
+                for (int f = 0; f < 8; ++f) u[f] = v[f] = 0.f;
 #pragma unroll 2
-            for (int j = 0; j < steps; ++j) {
-                const float2 wv = __ldg(ww + j * 32);
-                const float *pp = Pbuf + min(k0 + j, NC) * PT + ch * 8;
+                for (int j = 0; j < steps; ++j) {
+                    const float2 wv = __ldg(ww + j * 32);
+                    const float *pp = Pbuf + min(k0 + j, NC) * PT + ch * 8;
 #pragma unroll
-                for (int f = 0; f < 8; ++f) {
-                    const float x = pp[f];
-                    u[f] = fmaf(wv.x, x, u[f]);
-                    v[f] = fmaf(wv.y, x, v[f]);
+                    for (int f = 0; f < 8; ++f) {
+                        const float x = pp[f];
+                        u[f] = fmaf(wv.x, x, u[f]);
+                        v[f] = fmaf(wv.y, x, v[f]);
+                    }
+                }
+                if (sgm < nseg) {
+#pragma unroll
+                    for (int f = 0; f < 8; ++f) {
+                        s_U[sgm * PT + ch * 8 + f] = u[f];
+                        s_V[sgm * PT + ch * 8 + f] = v[f];
+                    }
                 }
             }
-            if (sgm < nseg) {
-#pragma unroll
-                for (int f = 0; f < 8; ++f) {
-                    s_U[sgm * PT + ch * 8 + f] = u[f];
-                    s_V[sgm * PT + ch * 8 + f] = v[f];
+            __syncthreads();
+            const int total = p.n_mels * TT;
+            for (int idx = tid; idx < total; idx += kThreads) {
+                const int t = idx % TT, m = idx / TT;
+                if (t0 + t < T) {
+                    const float v = s_U[m * PT + t] + s_V[(m + 1) * PT + t];
+                    vmax = fmaxf(vmax, v);
+                    out[(long long)m * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : v;
                 }
             }
-        }
-        __syncthreads();
-        const int total = p.n_mels * TT;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int t = idx % TT, m = idx / TT;
-            if (t0 + t < T) {
-                const float v = s_U[m * PT + t] + s_V[(m + 1) * PT + t];
-                vmax = fmaxf(vmax, v);
-                out[(long long)m * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : v;
-            }
-        }
-    } else {
-        constexpr int total = (NC + 1) * TT;
-        for (int idx = tid; idx < total; idx += kThreads) {
-            const int t = idx % TT, k = idx / TT;
-            if (t0 + t < T) {
-                const float v = Pbuf[k * PT + t];
-                vmax = fmaxf(vmax, v);
-                out[(long long)k * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v);
+        } else {
+            constexpr int total = (NC + 1) * TT;
+            for (int idx = tid; idx < total; idx += kThreads) {
+                const int t = idx % TT, k = idx / TT;
+                if (t0 + t < T) {
+                    const float v = Pbuf[k * PT + t];
+                    vmax = fmaxf(vmax, v);
+                    out[(long long)k * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v);
+                }
             }
         }
     }
@@ -1043,7 +1085,11 @@ static int launch_stft(const Plan &p, const StftParams &sp_in, int batch, int ma
     sp.tile_floats = tile_floats_for(TT, sp.hop, 2 * NC);
     const size_t smem = (size_t)(2 * NC + NC + sp.scr_floats + sp.tile_floats) * sizeof(float);
     if (smem > 227 * 1024) { set_error("hop_length / n_mels too large for the shared-memory tiles of this n_fft"); return AMTFEAT_ERR_INVALID; }
-    dim3 grid((maxT + TT - 1) / TT, batch);
+    // tiles per CTA: amortise the per-CTA prologue while keeping >= ~4 waves of 2 CTAs per SM
+    const int ntiles = (maxT + TT - 1) / TT;
+    const long long total_tiles = (long long)ntiles * batch;
+    sp.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, total_tiles / (148 * 2 * 4)));
+    dim3 grid((ntiles + sp.tiles_per_cta - 1) / sp.tiles_per_cta, batch);
     ProfScope ps(p, mel ? "stft_kernel_mel" : "stft_kernel_mag", st);
     if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);
     else stft_kernel<NC, MODE_STFT><<<grid, kThreads, smem, st>>>(sp);
