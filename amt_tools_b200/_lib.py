@@ -34,7 +34,7 @@ class AmtfeatError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            'libamtfeat.so is missing (%s). Build it with `python -m amt_tools_b200.build` '
+            'libamtfeat.so is missing (%s). Build it with `python amt_tools_b200/build.py` '
             '(needs nvcc); amt_tools_b200 has no CPU fallback.' % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     P = C.c_void_p
@@ -59,6 +59,10 @@ def _load():
         'amtfeat_process': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, P, C.c_size_t, P]),
         'amtfeat_process_host': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, C.c_int64, C.c_int64, P, P, P,
                                            C.c_size_t, P]),
+        'amtfeat_pipeline_create': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_size_t, C.POINTER(P)]),
+        'amtfeat_pipeline_submit': (C.c_int, [P, P, P, i64p, i64p, i64p, C.c_int, P, C.c_int64, C.c_int64, i64p]),
+        'amtfeat_pipeline_wait': (C.c_int, [P, C.c_int64]),
+        'amtfeat_pipeline_destroy': (None, [P]),
         'amtfeat_framify_hops': (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
         'amtfeat_framify': (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
         'amtfeat_profile_enable': (C.c_int, [P, C.c_int]),

@@ -1,6 +1,6 @@
 """
 Builds libamtfeat.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo
-snapshot to the GPU box).  `python -m amt_tools_b200.build` or __graft_entry__.build().
+snapshot to the GPU box).  `python amt_tools_b200/build.py` or __graft_entry__.build().
 """
 
 import os

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "plan.h"
 
@@ -162,6 +164,126 @@ int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const i
     if (rc != AMTFEAT_OK) return rc;
     e = cudaMemcpyAsync(h_out, d_out, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { amtfeat::set_error(std::string("D2H: ") + cudaGetErrorString(e)); return AMTFEAT_ERR_CUDA; }
+    return AMTFEAT_OK;
+}
+
+// ---- pipelined host executor -----------------------------------------------------------------------------------
+}  // extern "C"
+
+struct amtfeat_pipeline {
+    int device = 0, nslots = 0;
+    int64_t max_audio = 0, max_out = 0;
+    size_t max_ws = 0;
+    cudaStream_t s_h2d = nullptr, s_compute = nullptr, s_d2h = nullptr;
+    struct Slot {
+        float *d_audio = nullptr, *d_out = nullptr;
+        void *d_ws = nullptr;
+        cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+        int64_t ticket = -1;
+    };
+    std::vector<Slot> slots;
+    int64_t next_ticket = 0;
+};
+
+#define PIPE_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            amtfeat::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));       \
+            return AMTFEAT_ERR_CUDA;                                                      \
+        }                                                                                 \
+    } while (0)
+
+extern "C" {
+
+void amtfeat_pipeline_destroy(amtfeat_pipeline *pipe) {
+    if (!pipe) return;
+    cudaSetDevice(pipe->device);
+    if (pipe->s_d2h) cudaStreamSynchronize(pipe->s_d2h);
+    for (auto &s : pipe->slots) {
+        if (s.d_audio) cudaFree(s.d_audio);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_ws) cudaFree(s.d_ws);
+        if (s.uploaded) cudaEventDestroy(s.uploaded);
+        if (s.computed) cudaEventDestroy(s.computed);
+        if (s.downloaded) cudaEventDestroy(s.downloaded);
+    }
+    if (pipe->s_h2d) cudaStreamDestroy(pipe->s_h2d);
+    if (pipe->s_compute) cudaStreamDestroy(pipe->s_compute);
+    if (pipe->s_d2h) cudaStreamDestroy(pipe->s_d2h);
+    delete pipe;
+}
+
+static int pipeline_init(amtfeat_pipeline *p) {
+    PIPE_CUDA(cudaSetDevice(p->device));
+    PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
+    PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    for (auto &s : p->slots) {
+        PIPE_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_audio), (size_t)std::max<int64_t>(p->max_audio, 4) * sizeof(float)));
+        PIPE_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_out), (size_t)std::max<int64_t>(p->max_out, 4) * sizeof(float)));
+        PIPE_CUDA(cudaMalloc(&s.d_ws, std::max<size_t>(p->max_ws, 256)));
+        PIPE_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+        PIPE_CUDA(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+        PIPE_CUDA(cudaEventCreateWithFlags(&s.downloaded, cudaEventDisableTiming));
+    }
+    return AMTFEAT_OK;
+}
+
+int amtfeat_pipeline_create(int device, int nslots, int64_t max_audio_elems, int64_t max_out_elems, size_t max_workspace_bytes,
+                            amtfeat_pipeline **out) {
+    if (!out || nslots < 1 || nslots > 64 || max_audio_elems < 0 || max_out_elems < 0) { amtfeat::set_error("invalid pipeline arguments"); return AMTFEAT_ERR_INVALID; }
+    *out = nullptr;
+    if (device < 0) { amtfeat::set_error("a pipeline needs a CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
+    amtfeat_pipeline *p = new (std::nothrow) amtfeat_pipeline();
+    if (!p) { amtfeat::set_error("out of memory"); return AMTFEAT_ERR_INVALID; }
+    p->device = device; p->nslots = nslots; p->max_audio = max_audio_elems; p->max_out = max_out_elems; p->max_ws = max_workspace_bytes;
+    p->slots.resize(nslots);
+    const int rc = pipeline_init(p);
+    if (rc != AMTFEAT_OK) { amtfeat_pipeline_destroy(p); return rc; }
+    *out = p;
+    return AMTFEAT_OK;
+}
+
+int amtfeat_pipeline_submit(amtfeat_pipeline *pipe, const amtfeat_plan *plan, const float *h_audio, const int64_t *in_offsets,
+                            const int64_t *num_samples, const int64_t *out_offsets, int batch, float *h_out, int64_t audio_elems,
+                            int64_t out_elems, int64_t *ticket) {
+    if (!pipe || !plan) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    if (plan->p.device != pipe->device) { amtfeat::set_error("plan and pipeline live on different devices"); return AMTFEAT_ERR_INVALID; }
+    if (audio_elems > pipe->max_audio || out_elems > pipe->max_out) { amtfeat::set_error("batch larger than the pipeline's staging buffers"); return AMTFEAT_ERR_INVALID; }
+    const size_t ws = amtfeat::workspace_bytes(plan->p, batch, num_samples);
+    if (ws > pipe->max_ws) { amtfeat::set_error("batch needs a larger workspace than the pipeline was created with"); return AMTFEAT_ERR_WORKSPACE; }
+    PIPE_CUDA(cudaSetDevice(pipe->device));
+    amtfeat_pipeline::Slot &s = pipe->slots[pipe->next_ticket % pipe->nslots];
+    // upload: the kernels that last read this slot's audio must be done
+    PIPE_CUDA(cudaStreamWaitEvent(pipe->s_h2d, s.computed, 0));
+    PIPE_CUDA(cudaMemcpyAsync(s.d_audio, h_audio, (size_t)audio_elems * sizeof(float), cudaMemcpyHostToDevice, pipe->s_h2d));
+    PIPE_CUDA(cudaEventRecord(s.uploaded, pipe->s_h2d));
+    // compute: after the upload, and after the previous download of this slot's output
+    PIPE_CUDA(cudaStreamWaitEvent(pipe->s_compute, s.uploaded, 0));
+    PIPE_CUDA(cudaStreamWaitEvent(pipe->s_compute, s.downloaded, 0));
+    const int rc = amtfeat_process(plan, s.d_audio, in_offsets, num_samples, out_offsets, batch, s.d_out, s.d_ws, pipe->max_ws, pipe->s_compute);
+    if (rc != AMTFEAT_OK) return rc;
+    PIPE_CUDA(cudaEventRecord(s.computed, pipe->s_compute));
+    // download
+    PIPE_CUDA(cudaStreamWaitEvent(pipe->s_d2h, s.computed, 0));
+    PIPE_CUDA(cudaMemcpyAsync(h_out, s.d_out, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_d2h));
+    PIPE_CUDA(cudaEventRecord(s.downloaded, pipe->s_d2h));
+    s.ticket = pipe->next_ticket;
+    if (ticket) *ticket = pipe->next_ticket;
+    ++pipe->next_ticket;
+    return AMTFEAT_OK;
+}
+
+int amtfeat_pipeline_wait(amtfeat_pipeline *pipe, int64_t ticket) {
+    if (!pipe) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    PIPE_CUDA(cudaSetDevice(pipe->device));
+    if (ticket < 0 || ticket + pipe->nslots < pipe->next_ticket) {   // everything (or a ticket whose slot was already recycled)
+        PIPE_CUDA(cudaStreamSynchronize(pipe->s_d2h));
+        return AMTFEAT_OK;
+    }
+    if (ticket >= pipe->next_ticket) { amtfeat::set_error("unknown ticket"); return AMTFEAT_ERR_INVALID; }
+    PIPE_CUDA(cudaEventSynchronize(pipe->slots[ticket % pipe->nslots].downloaded));
     return AMTFEAT_OK;
 }
 

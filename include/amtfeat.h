@@ -137,6 +137,26 @@ AMTFEAT_API int amtfeat_process_host(const amtfeat_plan *plan, const float *h_au
                          int64_t audio_elems, int64_t out_elems, float *d_audio, float *d_out,
                          void *d_workspace, size_t workspace_bytes, void *stream);
 
+/*
+ * Pipelined host executor for bulk precompute (TranscriptionDataset.calculate_feats, datasets/common.py:212-295, applied to
+ * a whole corpus shard): three in-order streams (upload, compute, download) and `nslots` sets of device staging buffers,
+ * chained with events, so the download of batch i overlaps the kernels of batch i+1 and the upload of batch i+2 and the
+ * PCIe link stays busy in both directions.  Host buffers should be pinned.  One pipeline per GPU; plans of any module
+ * kind may share it (the plan is named per submission).
+ *   submit   enqueues H2D -> amtfeat_process -> D2H for one ragged batch and returns immediately with a ticket
+ *   wait     blocks until the features of that ticket (ticket < 0: everything submitted) are in h_out
+ * A slot's buffers are reused after `nslots` submissions; the event chain orders the reuse, the caller only has to keep
+ * h_audio / h_out alive until wait() returns.
+ */
+typedef struct amtfeat_pipeline amtfeat_pipeline;
+AMTFEAT_API int amtfeat_pipeline_create(int device, int nslots, int64_t max_audio_elems, int64_t max_out_elems,
+                                        size_t max_workspace_bytes, amtfeat_pipeline **out);
+AMTFEAT_API int amtfeat_pipeline_submit(amtfeat_pipeline *pipe, const amtfeat_plan *plan, const float *h_audio,
+                                        const int64_t *in_offsets, const int64_t *num_samples, const int64_t *out_offsets,
+                                        int batch, float *h_out, int64_t audio_elems, int64_t out_elems, int64_t *ticket);
+AMTFEAT_API int amtfeat_pipeline_wait(amtfeat_pipeline *pipe, int64_t ticket);
+AMTFEAT_API void amtfeat_pipeline_destroy(amtfeat_pipeline *pipe);
+
 /* Number of kernel launches amtfeat_process enqueues for this batch (bench.py's gpu_launches). */
 AMTFEAT_API int amtfeat_launch_count(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
 

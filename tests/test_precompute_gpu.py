@@ -53,3 +53,48 @@ def test_device_framify_matches_reference_restated():
         got = ab.framify_activations(torch.from_numpy(a).cuda(), win, hop, pad).cpu().numpy()
         want = _framify_reference(a, win, hop, pad)
         assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_pipeline_executor_matches_direct_calls():
+    """amtfeat_pipeline_* (upload / compute / download streams over staging slots) returns bit-identical features."""
+    import ctypes as C
+    from amt_tools_b200 import _lib
+    mods = [ab.MelSpec(16000), ab.HCQT(22050, 256, n_bins=120, bins_per_octave=24, harmonics=[0.5, 1, 2, 3])]
+    srs = [16000, 22050]
+    B = 3
+    jobs = []
+    for rep in range(5):            # more submissions than slots: buffers are recycled
+        for m, sr in zip(mods, srs):
+            n = 4 * ((sr * 2 + 500 * rep) // 4)
+            audio = np.stack([piano_like(n, sr, seed=900 + 10 * rep + b) for b in range(B)])
+            jobs.append((m, n, audio))
+    max_in = max(B * n for _, n, _ in jobs)
+    max_out = max(B * int(np.prod(m._out_shape(n))) for m, n, _ in jobs)
+    max_ws = max(int(_lib.lib.amtfeat_workspace_bytes(m._dev_plan.handle, B, _lib.i64_array([n] * B))) for m, n, _ in jobs)
+    pipe = C.c_void_p()
+    _lib.check(_lib.lib.amtfeat_pipeline_create(0, 2, max_in, max_out, max_ws, C.byref(pipe)))
+    try:
+        keep, tickets = [], []
+        for m, n, audio in jobs:
+            per = int(np.prod(m._out_shape(n)))
+            h_in = torch.from_numpy(audio).pin_memory()
+            h_out = torch.empty(B * per, dtype=torch.float32).pin_memory()
+            t = C.c_int64(-1)
+            _lib.check(_lib.lib.amtfeat_pipeline_submit(
+                pipe, m._dev_plan.handle, h_in.data_ptr(), _lib.i64_array([b * n for b in range(B)]), _lib.i64_array([n] * B),
+                _lib.i64_array([b * per for b in range(B)]), B, h_out.data_ptr(), h_in.numel(), h_out.numel(), C.byref(t)))
+            keep.append((h_in, h_out))
+            tickets.append(t.value)
+        assert tickets == list(range(len(jobs)))
+        _lib.check(_lib.lib.amtfeat_pipeline_wait(pipe, tickets[-1]))
+        _lib.check(_lib.lib.amtfeat_pipeline_wait(pipe, -1))
+        for (m, n, audio), (_, h_out) in zip(jobs, keep):
+            want = m.process_audio(audio).cpu()
+            assert torch.equal(h_out.view(want.shape), want)
+        # oversized batches are refused, not truncated
+        with pytest.raises(ValueError):
+            _lib.check(_lib.lib.amtfeat_pipeline_submit(
+                pipe, mods[0]._dev_plan.handle, keep[0][0].data_ptr(), _lib.i64_array([0]), _lib.i64_array([max_in + 4]),
+                _lib.i64_array([0]), 1, keep[0][1].data_ptr(), max_in + 4, 4, None))
+    finally:
+        _lib.lib.amtfeat_pipeline_destroy(pipe)
