@@ -354,7 +354,7 @@ static void build_fft_tables(Plan &p, int nfft) {
             double ang = -2.0 * kPi * (double)(k1 * n2) / (double)NC;
             t.tw1[k1 * R2 + n2] = {(float)std::cos(ang), (float)std::sin(ang)};
         }
-    t.tw2.resize(NC + 1);
+    t.tw2.assign(NC + 2, cfloat{0.f, 0.f});   // k = 0 .. NC, padded to a whole number of 16-byte granules
     for (int k = 0; k <= NC; ++k) {
         double ang = -kPi * (double)k / (double)NC;
         t.tw2[k] = {(float)std::cos(ang), (float)std::sin(ang)};

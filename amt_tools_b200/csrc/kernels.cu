@@ -621,7 +621,7 @@ struct CqtParams {
     const CqtRow *rows;
     const float2 *weights;
     const float2 *tw1, *tw2;
-    int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off, blk_off;
+    int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off, blk_off, region_floats, tiles_per_cta;
 };
 
 // Shared prologue of both CQT kernels: stage the level signal, run the warp FFT unit.
@@ -654,153 +654,211 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
     }
 }
 
-// Main kernel (n_fft >= 128).
+// Main kernel (n_fft >= 128).  A CTA walks `tiles_per_cta` consecutive tiles of one (clip, item): the twiddles are staged
+// once, and the audio of the next tile streams into its own shared-memory region (cp.async, zero fill) while the current
+// tile is projected and stored.
 // Phase A: per-warp FFT, then the real-FFT split restricted to the band [kmin, kmax] the item's rows touch; the band
-//          is written TRANSPOSED into Dbuf[k - kmin][frame] (frame fastest, pitch TT + 1), which aliases the audio tile.
+//          is written TRANSPOSED into Dbuf[k - kmin][frame] (frame fastest, pitch TT + 1), which aliases the FFT scratch.
 // Phase B: lanes run along frames, so every D fetch is a contiguous, conflict-free line; a group of FL lanes takes one
 //          block of up to 4 rows and streams its warp-uniform weights ([step][4 rows], two 16-byte loads per step):
-//          each D value feeds 4 complex MACs.  Results go through a staging tile (aliasing the FFT scratch) so that the
-//          global stores are T-contiguous.
+//          each D value feeds 4 complex MACs.  Results go through a staging tile (also inside the retired scratch) so
+//          that the global stores are T-contiguous (16-byte vectors when the clip's rows are 16-byte aligned).
 template <int NC>
 __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
-    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2;
+    constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2, NFFT = 2 * NC;
     constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
     constexpr int NSUB = kThreads / FL;         // lane groups per CTA
     constexpr int NCHUNK = TT / FL;             // frame chunks per tile
     constexpr int DP = TT + 1;                  // Dbuf pitch in float2 (odd: transposed writes are conflict free)
+    constexpr int SP = TT + 4;                  // staging pitch in floats (multiple of 4: 16-byte reads)
     extern __shared__ __align__(16) float smem[];
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
     float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
-    float *s_scr = reinterpret_cast<float *>(s_tw2 + NC + 2);         // 8 * WARP_PITCH; later the staging tile
-    float *s_tile = s_scr + kWarpsPerCta * L::WARP_PITCH;             // audio tile; later Dbuf
+    float *s_reg = reinterpret_cast<float *>(s_tw2 + NC + 2);         // FFT scratch; later staging | Dbuf | weights | blocks
+    float *s_tile = s_reg + p.region_floats;                          // audio tile (dedicated: prefetched during phase B)
     __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
     const int T = cm->T;
-    const int t0 = blockIdx.x * TT;
-    if (t0 >= T) return;
+    const int ntiles = (T + TT - 1) / TT;
+    const int tile_begin = blockIdx.x * p.tiles_per_cta;
+    if (tile_begin >= ntiles) return;
+    const int tile_end = min(ntiles, tile_begin + p.tiles_per_cta);
     const CqtItem it = p.items[blockIdx.z];
+    const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
+    const long long len = cm->lvl_len[it.level];
+    const bool overlap = it.hop <= NFFT;
     if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
-    cqt_fft_phase<NC>(p, it, cm, t0, s_tw1, s_tw2, s_scr, s_tile);
 
-    // Phase-B layout of the combined [scratch | tile] region: staging tile + row offsets, then Dbuf, then the item's weights
-    float *s_stage = s_scr;
-    int *s_rowoff = reinterpret_cast<int *>(s_stage + p.stage_blocks * 4 * (TT + 1));
-    float2 *Dbuf = reinterpret_cast<float2 *>(s_scr + p.dbuf_off);
-    float4 *s_w = reinterpret_cast<float4 *>(s_scr + p.w_off);
-    const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_scr + p.blk_off);   // the item's block descriptors
-    {   // real-FFT split on the band, held in registers across the barrier that retires the scratch and the audio tile
-        const float2 *scr = reinterpret_cast<const float2 *>(s_scr) + warp * WP2;
-        const int kb = it.kmax - it.kmin + 1;
-        constexpr int JB = (NC + 1 + 31) / 32;
-        float2 X[G][JB];
+    // prologue: twiddles and the first audio tile, all asynchronous (one exposed latency instead of three)
+    {
+        const float4 *g1 = reinterpret_cast<const float4 *>(p.tw1), *g2 = reinterpret_cast<const float4 *>(p.tw2);
+        for (int i = tid; i < NC / 2; i += kThreads) {
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float4 *>(s_tw1) + i));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(g1 + i) : "memory");
+        }
+        for (int i = tid; i < (NC + 2) / 2; i += kThreads) {   // the table is padded to NC + 2 entries on the host
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<float4 *>(s_tw2) + i));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(g2 + i) : "memory");
+        }
+    }
+    int shift = 0, fstride = overlap ? it.hop : NFFT;
+    if (overlap) load_tile_async(s_tile, src, len, (long long)tile_begin * TT * it.hop - NC, it.hop, NFFT, TT, tid, shift);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+
+    // phase-B layout of the region
+    float *s_stage = s_reg;
+    float2 *Dbuf = reinterpret_cast<float2 *>(s_reg + p.dbuf_off);
+    float4 *s_w = reinterpret_cast<float4 *>(s_reg + p.w_off);
+    const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_reg + p.blk_off);   // the item's block descriptors
+    float *out = p.out + cm->out_off;
+    const bool vec_store = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int sub = tid / FL, lt = tid % FL;
+    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
+    const int kb = it.kmax - it.kmin + 1;
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int t0 = tile * TT;
+        if (overlap) {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();   // previous iteration's readers of the region are done
+            load_tile(s_tile, src, len, (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
+        }
+        __syncthreads();       // tile (and, first time, the twiddles) visible; previous iteration's staging retired
+
+        float2 *scr = reinterpret_cast<float2 *>(s_reg) + warp * WP2;
+        if (((shift | fstride) & 1) == 0) {
+            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                return *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
+            });
+        } else {
+            warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
+                const float *x = s_tile + shift + (warp * G + g) * fstride + 2 * n;
+                return make_float2(x[0], x[1]);
+            });
+        }
+
+        {   // real-FFT split on the band, held in registers across the barrier that retires the scratch and the audio tile
+            constexpr int JB = (NC + 1 + 31) / 32;
+            float2 X[G][JB];
 #pragma unroll
-        for (int g = 0; g < G; ++g)
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int j = 0; j < JB; ++j) {
-                const int kk = lane + 32 * j;
-                if (kk < kb) {
-                    const int k = it.kmin + kk;
-                    const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
-                    float2 E, Tw;
-                    rfft_split(A, B, AMT_TW_GLOBAL ? __ldg(p.tw2 + k) : s_tw2[k], E, Tw);
-                    X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
+                for (int j = 0; j < JB; ++j) {
+                    const int kk = lane + 32 * j;
+                    if (kk < kb) {
+                        const int k = it.kmin + kk;
+                        const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
+                        float2 E, Tw;
+                        rfft_split(A, B, s_tw2[k], E, Tw);
+                        X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
+                    }
                 }
-            }
-        __syncthreads();
-        // stream the item's weights into shared memory (asynchronously, L1 bypass) while D is being written
-        {
-            const float4 *src = p.weights4 + it.woff0;
-            for (int i = tid; i < it.wcount; i += kThreads) {
-                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_w + i));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + i) : "memory");
-            }
-            {   // ... and its block descriptors (112 B each, 16-byte granules)
+            __syncthreads();
+            // stream the item's weights and block descriptors into the retired scratch (L1 bypass) while D is being written,
+            // then the next tile's audio into the tile region (a second group: phase B only waits for the first)
+            {
+                const float4 *wsrc = p.weights4 + it.woff0;
+                for (int i = tid; i < it.wcount; i += kThreads) {
+                    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_w + i));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(wsrc + i) : "memory");
+                }
                 const float4 *bsrc = reinterpret_cast<const float4 *>(p.blocks + it.blk0);
                 const int n16 = it.nblk * (int)(sizeof(CqtBlock4) / 16);
                 for (int i = tid; i < n16; i += kThreads) {
                     const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<const float4 *>(s_blk) + i));
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(bsrc + i) : "memory");
                 }
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+                if (overlap && tile + 1 < tile_end)
+                    load_tile_async(s_tile, src, len, (long long)(t0 + TT) * it.hop - NC, it.hop, NFFT, TT, tid, shift);
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-        }
 #pragma unroll
-        for (int g = 0; g < G; ++g)
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int j = 0; j < JB; ++j) {
-                const int kk = lane + 32 * j;
-                if (kk < kb) Dbuf[kk * DP + warp * G + g] = X[g][j];
-            }
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    float *out = p.out + cm->out_off;
-    const int sub = tid / FL, lt = tid % FL;
-    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
-    for (int b0 = 0; b0 < it.nblk; b0 += p.stage_blocks) {
-        const int nb = min(p.stage_blocks, it.nblk - b0);
-        for (int rs = tid; rs < nb * 4 * kMaxDst; rs += kThreads) {   // s_rowoff[(block row)][destination]
-            const int d = rs % kMaxDst, br = rs / kMaxDst;
-            s_rowoff[rs] = s_blk[b0 + (br >> 2)].off[d][br & 3];
-        }
-        for (int w = sub; w < nb * NCHUNK; w += NSUB) {
-            const int bi = w / NCHUNK, ch = w % NCHUNK;
-            const CqtBlock4 *bl = s_blk + b0 + bi;
-            const int steps = bl->steps;
-            const float4 *wt = s_w + (bl->woff - it.woff0);
-            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
-            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll 4
-            for (int s = 0; s < steps; ++s) {
-                const float2 d = Dp[s * DP];
-                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
-                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
-                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
-                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
-                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
-                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
-                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
-                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
-                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
-            }
-            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
-                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
-            const int t = ch * FL + lt;
-            float *st = s_stage + (bi * 4) * (TT + 1) + t;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) st[r * (TT + 1)] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-            if (p.decibels) {
-                float vmax = (t0 + t < T) ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
-#pragma unroll
-                for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                if (lt == 0)
-                    for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
-            }
+                for (int j = 0; j < JB; ++j) {
+                    const int kk = lane + 32 * j;
+                    if (kk < kb) Dbuf[kk * DP + warp * G + g] = X[g][j];
+                }
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         }
         __syncthreads();
-        for (int idx = tid; idx < nb * 4 * TT; idx += kThreads) {
-            const int t = idx % TT, rs = idx / TT;
-            if (t0 + t < T) {
-                const float v = s_stage[rs * (TT + 1) + t];
-                // rows shared by several harmonics are stored to each of them (the list is -1 terminated)
-                int off = s_rowoff[rs * kMaxDst];
-                if (off >= 0) {
-                    out[(long long)off * T + t0 + t] = v;
+
+        for (int b0 = 0; b0 < it.nblk; b0 += p.stage_blocks) {
+            const int nb = min(p.stage_blocks, it.nblk - b0);
+            for (int w = sub; w < nb * NCHUNK; w += NSUB) {
+                const int bi = w / NCHUNK, ch = w % NCHUNK;
+                const CqtBlock4 *bl = s_blk + b0 + bi;
+                const int steps = bl->steps;
+                const float4 *wt = s_w + (bl->woff - it.woff0);
+                const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
+                float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 4
+                for (int s = 0; s < steps; ++s) {
+                    const float2 d = Dp[s * DP];
+                    const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
+                    a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
+                    a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
+                    a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
+                    a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
+                    a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
+                    a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
+                    a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
+                    a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
+                }
+                const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
+                                     fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
+                const int t = ch * FL + lt;
+                float *st = s_stage + (bi * 4) * SP + t;
 #pragma unroll
-                    for (int d = 1; d < kMaxDst; ++d) {
-                        off = s_rowoff[rs * kMaxDst + d];
+                for (int r = 0; r < 4; ++r) st[r * SP] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
+                if (p.decibels) {
+                    float vmax = (t0 + t < T) ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
+#pragma unroll
+                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
+                    if (lt == 0)
+                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+                }
+            }
+            __syncthreads();
+            // rows shared by several harmonics are stored to each of them (the destination list is -1 terminated)
+            if (vec_store && t0 + TT <= T) {
+                constexpr int QT = TT / 4;
+                for (int idx = tid; idx < nb * 4 * QT; idx += kThreads) {
+                    const int q = idx % QT, rs = idx / QT;
+                    const float4 v = *reinterpret_cast<const float4 *>(s_stage + rs * SP + 4 * q);
+                    const CqtBlock4 *bl = s_blk + b0 + (rs >> 2);
+#pragma unroll
+                    for (int d = 0; d < kMaxDst; ++d) {
+                        const int off = bl->off[d][rs & 3];
                         if (off < 0) break;
-                        out[(long long)off * T + t0 + t] = v;
+                        *reinterpret_cast<float4 *>(out + (long long)off * T + t0 + 4 * q) = v;
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < nb * 4 * TT; idx += kThreads) {
+                    const int t = idx % TT, rs = idx / TT;
+                    if (t0 + t < T) {
+                        const float v = s_stage[rs * SP + t];
+                        const CqtBlock4 *bl = s_blk + b0 + (rs >> 2);
+#pragma unroll
+                        for (int d = 0; d < kMaxDst; ++d) {
+                            const int off = bl->off[d][rs & 3];
+                            if (off < 0) break;
+                            out[(long long)off * T + t0 + t] = v;
+                        }
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
 
@@ -1113,24 +1171,37 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     const FftTables &ft = p.fft.at(NC);
     cp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1);
     cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
-    dim3 grid((maxT + TT - 1) / TT, batch, nitems);
+    const int ntiles = (maxT + TT - 1) / TT;
+    dim3 grid(ntiles, batch, nitems);
     static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
     size_t smem;
     if (cqt_use_blocks<NC>()) {
-        // phase B reuses the [FFT scratch | audio tile] region: staging tile + row offsets, Dbuf, the item's weights
+        // phase B reuses the retired FFT scratch: staging tile | Dbuf | the item's weights | its block descriptors.  The audio
+        // tile keeps its own region so that the next tile can stream in during phase B.
         const int scratch_floats = kWarpsPerCta * L::WARP_PITCH;
+        const int fixed_floats = 2 * NC + 2 * (NC + 2);
         int maxw = 0;
         for (int i = item0; i < item0 + nitems; ++i) maxw = std::max(maxw, p.items[i].wcount);
-        cp.stage_blocks = std::max(1, std::min(maxblk, 4096 / (4 * (TT + 1))));
-        cp.stage_rows = 0;
-        const int stage_floats = (cp.stage_blocks * 4 * (TT + 1 + kMaxDst) + 3) / 4 * 4;
         const int dbuf_floats = (maxkb * (TT + 1) * 2 + 3) / 4 * 4;
+        const int blk_floats = maxblk * (int)(sizeof(CqtBlock4) / 4);
+        const int per_block = 4 * (TT + 4);
+        // as many staged blocks as fit next to the rest without growing past the scratch or, failing that, past the size
+        // that still lets two CTAs share an SM (at least one block)
+        const int rest = dbuf_floats + maxw * 4 + blk_floats;
+        const int two_cta_floats = (int)((113 * 1024) / sizeof(float)) - 256 - fixed_floats - cp.tile_floats;
+        int room = std::max(scratch_floats, two_cta_floats) - rest;
+        cp.stage_blocks = std::max(1, std::min({maxblk, room / per_block, 8192 / per_block}));
+        cp.stage_rows = 0;
+        const int stage_floats = cp.stage_blocks * per_block;
         cp.dbuf_off = stage_floats;
         cp.w_off = stage_floats + dbuf_floats;
         cp.blk_off = cp.w_off + maxw * 4;
-        const int need = cp.blk_off + maxblk * (int)(sizeof(CqtBlock4) / 4);
-        cp.tile_floats = std::max(cp.tile_floats, (need - scratch_floats + 3) / 4 * 4);
-        smem = (size_t)(2 * NC + 2 * (NC + 2) + scratch_floats + cp.tile_floats) * sizeof(float);
+        cp.region_floats = (std::max(scratch_floats, cp.blk_off + blk_floats) + 3) / 4 * 4;
+        smem = (size_t)(fixed_floats + cp.region_floats + cp.tile_floats) * sizeof(float);
+        // tiles per CTA: amortise the per-CTA prologue while keeping >= ~4 waves of 2 CTAs per SM
+        const long long total = (long long)ntiles * batch * nitems;
+        cp.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, total / (148 * 2 * 4)));
+        grid.x = (ntiles + cp.tiles_per_cta - 1) / cp.tiles_per_cta;
     } else {
         cp.stage_blocks = 0;
         cp.stage_rows = std::max(1, std::min(maxrows, 3072 / (TT + 1)));
