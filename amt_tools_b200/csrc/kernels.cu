@@ -17,10 +17,22 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "fft_device.cuh"
 #include "plan.h"
+
+// A/B knobs (tools/variants.py); the defaults are the shipped configuration
+#ifndef AMT_CQT_TPC_MAX
+#define AMT_CQT_TPC_MAX 8      // most tiles one CQT CTA walks
+#endif
+#ifndef AMT_CQT_WAVES
+#define AMT_CQT_WAVES 4        // ... while keeping at least this many waves of CTAs
+#endif
+#ifndef AMT_DBG_SKIP
+#define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
+#endif
 
 namespace amtfeat {
 
@@ -671,11 +683,10 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     constexpr int NSUB = kThreads / FL;         // lane groups per CTA
     constexpr int NCHUNK = TT / FL;             // frame chunks per tile
     constexpr int DP = TT + 1;                  // Dbuf pitch in float2 (odd: transposed writes are conflict free)
-    constexpr int SP = TT + 4;                  // staging pitch in floats (multiple of 4: 16-byte reads)
     extern __shared__ __align__(16) float smem[];
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
     float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
-    float *s_reg = reinterpret_cast<float *>(s_tw2 + NC + 2);         // FFT scratch; later staging | Dbuf | weights | blocks
+    float *s_reg = reinterpret_cast<float *>(s_tw2 + NC + 2);         // FFT scratch; later Dbuf | weights | blocks
     float *s_tile = s_reg + p.region_floats;                          // audio tile (dedicated: prefetched during phase B)
     __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
 
@@ -709,12 +720,10 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 
     // phase-B layout of the region
-    float *s_stage = s_reg;
     float2 *Dbuf = reinterpret_cast<float2 *>(s_reg + p.dbuf_off);
     float4 *s_w = reinterpret_cast<float4 *>(s_reg + p.w_off);
     const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_reg + p.blk_off);   // the item's block descriptors
     float *out = p.out + cm->out_off;
-    const bool vec_store = ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int sub = tid / FL, lt = tid % FL;
     const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
     const int kb = it.kmax - it.kmin + 1;
@@ -731,7 +740,8 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
         __syncthreads();       // tile (and, first time, the twiddles) visible; previous iteration's staging retired
 
         float2 *scr = reinterpret_cast<float2 *>(s_reg) + warp * WP2;
-        if (((shift | fstride) & 1) == 0) {
+        if (AMT_DBG_SKIP & 2) {
+        } else if (((shift | fstride) & 1) == 0) {
             warp_fft_unit<NC>(scr, s_tw1, lane, [&](int g, int n) {
                 return *reinterpret_cast<const float2 *>(s_tile + shift + (warp * G + g) * fstride + 2 * n);
             });
@@ -742,22 +752,28 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
             });
         }
 
-        {   // real-FFT split on the band, held in registers across the barrier that retires the scratch and the audio tile
+        // Real-FFT split on the band, held in registers across the barrier that retires the scratch, then written transposed
+        // into Dbuf.  Only the first nj = ceil(kb / 32) register columns are touched (warp-uniform early exit).
+        {
             constexpr int JB = (NC + 1 + 31) / 32;
-            float2 X[G][JB];
+            const int nj = (kb + 31) >> 5;
+            float2 X[JB][G];
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+            for (int j = 0; j < JB; ++j) {
+                if (j >= nj) break;
+                const int kk = lane + 32 * j;
+                if (kk < kb) {
+                    const int k = it.kmin + kk;
+                    const float2 tw = s_tw2[k];
 #pragma unroll
-                for (int j = 0; j < JB; ++j) {
-                    const int kk = lane + 32 * j;
-                    if (kk < kb) {
-                        const int k = it.kmin + kk;
+                    for (int g = 0; g < G; ++g) {
                         const float2 A = scr[g * S + (k & (NC - 1))], B = scr[g * S + ((NC - k) & (NC - 1))];
                         float2 E, Tw;
-                        rfft_split(A, B, s_tw2[k], E, Tw);
-                        X[g][j] = make_float2(E.x + Tw.x, E.y + Tw.y);
+                        rfft_split(A, B, tw, E, Tw);
+                        X[j][g] = make_float2(E.x + Tw.x, E.y + Tw.y);
                     }
                 }
+            }
             __syncthreads();
             // stream the item's weights and block descriptors into the retired scratch (L1 bypass) while D is being written,
             // then the next tile's audio into the tile region (a second group: phase B only waits for the first)
@@ -779,85 +795,68 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
 #pragma unroll
-            for (int g = 0; g < G; ++g)
+            for (int j = 0; j < JB; ++j) {
+                if (j >= nj) break;
+                const int kk = lane + 32 * j;
+                if (kk < kb) {
 #pragma unroll
-                for (int j = 0; j < JB; ++j) {
-                    const int kk = lane + 32 * j;
-                    if (kk < kb) Dbuf[kk * DP + warp * G + g] = X[g][j];
+                    for (int g = 0; g < G; ++g) Dbuf[kk * DP + warp * G + g] = X[j][g];
                 }
+            }
             asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         }
         __syncthreads();
 
-        for (int b0 = 0; b0 < it.nblk; b0 += p.stage_blocks) {
-            const int nb = min(p.stage_blocks, it.nblk - b0);
-            for (int w = sub; w < nb * NCHUNK; w += NSUB) {
-                const int bi = w / NCHUNK, ch = w % NCHUNK;
-                const CqtBlock4 *bl = s_blk + b0 + bi;
-                const int steps = bl->steps;
-                const float4 *wt = s_w + (bl->woff - it.woff0);
-                const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
-                float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        // Projection.  The lanes of a group hold consecutive frames, so the stores of one row are already T-contiguous
+        // (FL * 4 bytes per row and group): results go straight to global memory.
+        for (int w = sub; w < it.nblk * NCHUNK; w += NSUB) {
+            const int bi = w / NCHUNK, ch = w % NCHUNK;
+            const CqtBlock4 *bl = s_blk + bi;
+            const int steps = bl->steps;
+            const float4 *wt = s_w + (bl->woff - it.woff0);
+            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll 4
-                for (int s = 0; s < steps; ++s) {
-                    const float2 d = Dp[s * DP];
-                    const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
-                    a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
-                    a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
-                    a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
-                    a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
-                    a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
-                    a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
-                    a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
-                    a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
-                }
-                const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
-                                     fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
-                const int t = ch * FL + lt;
-                float *st = s_stage + (bi * 4) * SP + t;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) st[r * SP] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-                if (p.decibels) {
-                    float vmax = (t0 + t < T) ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
-#pragma unroll
-                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                    if (lt == 0)
-                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
-                }
+            for (int s = 0; s < ((AMT_DBG_SKIP & 1) ? 1 : steps); ++s) {
+                const float2 d = Dp[s * DP];
+                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
+                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
+                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
+                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
+                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
+                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
+                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
+                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
+                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
             }
-            __syncthreads();
-            // rows shared by several harmonics are stored to each of them (the destination list is -1 terminated)
-            if (vec_store && t0 + TT <= T) {
-                constexpr int QT = TT / 4;
-                for (int idx = tid; idx < nb * 4 * QT; idx += kThreads) {
-                    const int q = idx % QT, rs = idx / QT;
-                    const float4 v = *reinterpret_cast<const float4 *>(s_stage + rs * SP + 4 * q);
-                    const CqtBlock4 *bl = s_blk + b0 + (rs >> 2);
+            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
+                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
+            const int t = t0 + ch * FL + lt;
+            const bool live = t < T;
+            if (live) {
+                // rows shared by several harmonics are stored to each of them (the destination list is -1 terminated)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float v = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
 #pragma unroll
                     for (int d = 0; d < kMaxDst; ++d) {
-                        const int off = bl->off[d][rs & 3];
+                        const int off = bl->off[d][r];
                         if (off < 0) break;
-                        *reinterpret_cast<float4 *>(out + (long long)off * T + t0 + 4 * q) = v;
-                    }
-                }
-            } else {
-                for (int idx = tid; idx < nb * 4 * TT; idx += kThreads) {
-                    const int t = idx % TT, rs = idx / TT;
-                    if (t0 + t < T) {
-                        const float v = s_stage[rs * SP + t];
-                        const CqtBlock4 *bl = s_blk + b0 + (rs >> 2);
-#pragma unroll
-                        for (int d = 0; d < kMaxDst; ++d) {
-                            const int off = bl->off[d][rs & 3];
-                            if (off < 0) break;
-                            out[(long long)off * T + t0 + t] = v;
-                        }
+                        out[(long long)off * T + t] = v;
                     }
                 }
             }
-            __syncthreads();
+            if (p.decibels) {
+                float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
+#pragma unroll
+                for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
+                if (lt == 0)
+                    for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+            }
         }
+        // no barrier here: the next iteration's top-of-loop barrier orders these reads before the next FFT's scratch writes
     }
+    __syncthreads();
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
@@ -1176,7 +1175,7 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
     size_t smem;
     if (cqt_use_blocks<NC>()) {
-        // phase B reuses the retired FFT scratch: staging tile | Dbuf | the item's weights | its block descriptors.  The audio
+        // phase B reuses the retired FFT scratch: Dbuf | the item's weights | its block descriptors.  The audio
         // tile keeps its own region so that the next tile can stream in during phase B.
         const int scratch_floats = kWarpsPerCta * L::WARP_PITCH;
         const int fixed_floats = 2 * NC + 2 * (NC + 2);
@@ -1184,23 +1183,16 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
         for (int i = item0; i < item0 + nitems; ++i) maxw = std::max(maxw, p.items[i].wcount);
         const int dbuf_floats = (maxkb * (TT + 1) * 2 + 3) / 4 * 4;
         const int blk_floats = maxblk * (int)(sizeof(CqtBlock4) / 4);
-        const int per_block = 4 * (TT + 4);
-        // as many staged blocks as fit next to the rest without growing past the scratch or, failing that, past the size
-        // that still lets two CTAs share an SM (at least one block)
-        const int rest = dbuf_floats + maxw * 4 + blk_floats;
-        const int two_cta_floats = (int)((113 * 1024) / sizeof(float)) - 256 - fixed_floats - cp.tile_floats;
-        int room = std::max(scratch_floats, two_cta_floats) - rest;
-        cp.stage_blocks = std::max(1, std::min({maxblk, room / per_block, 8192 / per_block}));
+        cp.stage_blocks = 0;
         cp.stage_rows = 0;
-        const int stage_floats = cp.stage_blocks * per_block;
-        cp.dbuf_off = stage_floats;
-        cp.w_off = stage_floats + dbuf_floats;
+        cp.dbuf_off = 0;
+        cp.w_off = dbuf_floats;
         cp.blk_off = cp.w_off + maxw * 4;
         cp.region_floats = (std::max(scratch_floats, cp.blk_off + blk_floats) + 3) / 4 * 4;
         smem = (size_t)(fixed_floats + cp.region_floats + cp.tile_floats) * sizeof(float);
         // tiles per CTA: amortise the per-CTA prologue while keeping >= ~4 waves of 2 CTAs per SM
         const long long total = (long long)ntiles * batch * nitems;
-        cp.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, total / (148 * 2 * 4)));
+        cp.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(AMT_CQT_TPC_MAX, total / (148 * 2 * AMT_CQT_WAVES)));
         grid.x = (ntiles + cp.tiles_per_cta - 1) / cp.tiles_per_cta;
     } else {
         cp.stage_blocks = 0;
