@@ -675,7 +675,7 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
 //          block of up to 4 rows and streams its warp-uniform weights ([step][4 rows], two 16-byte loads per step):
 //          each D value feeds 4 complex MACs.  Results go through a staging tile (also inside the retired scratch) so
 //          that the global stores are T-contiguous (16-byte vectors when the clip's rows are 16-byte aligned).
-template <int NC>
+template <int NC, bool HALF>
 __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2, NFFT = 2 * NC;
@@ -755,7 +755,8 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
         // Real-FFT split on the band, held in registers across the barrier that retires the scratch, then written transposed
         // into Dbuf.  Only the first nj = ceil(kb / 32) register columns are touched (warp-uniform early exit).
         {
-            constexpr int JB = (NC + 1 + 31) / 32;
+            // HALF: every item of the launch has a band of at most half the spectrum (the host checks) -> half the registers
+            constexpr int JFULL = (NC + 1 + 31) / 32, JB = HALF ? (JFULL + 1) / 2 : JFULL;
             const int nj = (kb + 31) >> 5;
             float2 X[JB][G];
 #pragma unroll
@@ -847,11 +848,17 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 }
             }
             if (p.decibels) {
+                // per-(clip, harmonic) maximum: publish only when some frame of the group exceeds what the CTA already holds
+                // (s_max only grows, so a stale read merely publishes once more)
                 float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
+                int have = s_max[bl->chan[0]];
+                for (int d = 1; d < bl->ndst; ++d) have = min(have, s_max[bl->chan[d]]);
+                if (__any_sync(gmask, __float_as_int(vmax) > have)) {
 #pragma unroll
-                for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                if (lt == 0)
-                    for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
+                    if (lt == 0)
+                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+                }
             }
         }
         // no barrier here: the next iteration's top-of-loop barrier orders these reads before the next FFT's scratch writes
@@ -987,7 +994,11 @@ template <int NC> static size_t cqt_smem(int tile_floats, int stage_rows) {
 }
 template <int NC> static constexpr bool cqt_use_blocks() { return NC >= 64; }
 template <int NC> static cudaError_t cqt_set_attr() {
-    if (cqt_use_blocks<NC>()) return cudaFuncSetAttribute(cqt_kernel<(NC >= 64 ? NC : 64)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (cqt_use_blocks<NC>()) {
+        cudaError_t e = cudaFuncSetAttribute(cqt_kernel<(NC >= 64 ? NC : 64), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(cqt_kernel<(NC >= 64 ? NC : 64), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    }
     return cudaFuncSetAttribute(cqt_small_kernel<(NC < 64 ? NC : 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
 }
 static int tile_floats_for(int TT, int hop, int nfft) {
@@ -1201,7 +1212,11 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     }
     if (smem > 226 * 1024) { set_error("hop_length too large for the shared-memory audio tile"); return AMTFEAT_ERR_INVALID; }
     ProfScope ps(p, nm.c_str(), st);
-    if (cqt_use_blocks<NC>()) cqt_kernel<(NC >= 64 ? NC : 64)><<<grid, kThreads, smem, st>>>(cp);
+    if (cqt_use_blocks<NC>()) {
+        constexpr int JFULL = (NC + 1 + 31) / 32;
+        if ((maxkb + 31) / 32 <= (JFULL + 1) / 2) cqt_kernel<(NC >= 64 ? NC : 64), true><<<grid, kThreads, smem, st>>>(cp);
+        else cqt_kernel<(NC >= 64 ? NC : 64), false><<<grid, kThreads, smem, st>>>(cp);
+    }
     else cqt_small_kernel<(NC < 64 ? NC : 32)><<<grid, kThreads, smem, st>>>(cp);
     AMT_CUDA(cudaGetLastError());
     return AMTFEAT_OK;
