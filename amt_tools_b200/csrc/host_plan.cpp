@@ -605,8 +605,14 @@ static int build_vqt(Plan &p) {
                         w[2 * r + 1] = v.y;
                     }
                 }
+#if AMT_PROJ_PACKED
+                // row pairs side by side: (re0, re1, im0, im1), (re2, re3, im2, im3) -- operands of the packed FFMA2 projection
+                p.weights4[(size_t)bl.woff + 2 * st] = cfloat4{w[0], w[2], w[1], w[3]};
+                p.weights4[(size_t)bl.woff + 2 * st + 1] = cfloat4{w[4], w[6], w[5], w[7]};
+#else
                 p.weights4[(size_t)bl.woff + 2 * st] = cfloat4{w[0], w[1], w[2], w[3]};
                 p.weights4[(size_t)bl.woff + 2 * st + 1] = cfloat4{w[4], w[5], w[6], w[7]};
+#endif
             }
             it.kmin = std::min(it.kmin, lo);
             it.kmax = std::max(it.kmax, hi - 1);

@@ -816,6 +816,27 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
             const int steps = bl->steps;
             const float4 *wt = s_w + (bl->woff - it.woff0);
             const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
+#if AMT_PROJ_PACKED
+            // two rows per packed FFMA2: weights (re0, re1 | im0, im1), (re2, re3 | im2, im3); D broadcast to both halves
+            const float2 z2 = make_float2(0.f, 0.f);
+            float2 re01 = z2, ng01 = z2, ia01 = z2, ib01 = z2, re23 = z2, ng23 = z2, ia23 = z2, ib23 = z2;
+#pragma unroll 4
+            for (int s = 0; s < ((AMT_DBG_SKIP & 1) ? 1 : steps); ++s) {
+                const float2 d = Dp[s * DP];
+                const float4 wa = wt[2 * s], wb = wt[2 * s + 1];
+                const float2 dxx = make_float2(d.x, d.x), dyy = make_float2(d.y, d.y);
+                re01 = ffma2(make_float2(wa.x, wa.y), dxx, re01);
+                ng01 = ffma2(make_float2(wa.z, wa.w), dyy, ng01);
+                ia01 = ffma2(make_float2(wa.x, wa.y), dyy, ia01);
+                ib01 = ffma2(make_float2(wa.z, wa.w), dxx, ib01);
+                re23 = ffma2(make_float2(wb.x, wb.y), dxx, re23);
+                ng23 = ffma2(make_float2(wb.z, wb.w), dyy, ng23);
+                ia23 = ffma2(make_float2(wb.x, wb.y), dyy, ia23);
+                ib23 = ffma2(make_float2(wb.z, wb.w), dxx, ib23);
+            }
+            const float2 a0 = make_float2(re01.x - ng01.x, ia01.x + ib01.x), a1 = make_float2(re01.y - ng01.y, ia01.y + ib01.y);
+            const float2 a2 = make_float2(re23.x - ng23.x, ia23.x + ib23.x), a3 = make_float2(re23.y - ng23.y, ia23.y + ib23.y);
+#else
             float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll 4
             for (int s = 0; s < ((AMT_DBG_SKIP & 1) ? 1 : steps); ++s) {
@@ -830,6 +851,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
                 a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
             }
+#endif
             const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
                                  fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
             const int t = t0 + ch * FL + lt;
@@ -1300,6 +1322,8 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         const bool fast = !p.decim_hh.empty() && !p.decim_direct;
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
+            // (both forms have a ~28 us latency floor per launch on the short, deep levels: one warp runs three 1024-point
+            // transforms back to back / one thread runs 16 x 389 MACs; mixing the forms per level was measured and is no faster)
             if (fast) {
                 using L = FftLayout<1024>;
                 DecFftParams dp{};

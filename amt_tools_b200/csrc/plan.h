@@ -9,6 +9,11 @@
 
 #include "../../include/amtfeat.h"
 
+// Layout of the CQT block weights: 1 = row pairs side by side for the packed (FFMA2) projection, 0 = row-major complex.
+#ifndef AMT_PROJ_PACKED
+#define AMT_PROJ_PACKED 1
+#endif
+
 namespace amtfeat {
 
 constexpr int kMaxLevels = 16;      // ladder depth (octaves + early downsampling)
