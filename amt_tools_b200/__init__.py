@@ -12,5 +12,6 @@ from . import _lib  # noqa: F401  (fails loudly when libamtfeat.so has not been 
 from . import features
 from .features import (FeatureCombo, FeatureModule, CQT, HCQT, HVQT, MelSpec, SignalPower, STFT, VQT,
                        WaveformWrapper, framify_activations)
+from .stream import AudioStream, FeatureStream
 
 __version__ = '0.1.0'
