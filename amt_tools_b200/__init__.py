@@ -13,5 +13,7 @@ from . import features
 from .features import (FeatureCombo, FeatureModule, CQT, HCQT, HVQT, MelSpec, SignalPower, STFT, VQT,
                        WaveformWrapper, framify_activations)
 from .stream import AudioStream, FeatureStream
+from . import ingest
+from .ingest import load_normalize_audio, resample, rms_norm, to_mono
 
 __version__ = '0.1.0'

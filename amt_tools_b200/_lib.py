@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get('AMTFEAT_LIB') or os.path.join(_HERE, 'libamtfeat.so')
 MAX_HARMONICS = 16
 (WAVEFORM, STFT, MEL, VQT, HVQT, POWER) = range(6)
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WORKSPACE = range(5)
+RES_KAISER_BEST, RES_KAISER_FAST = range(2)
 
 
 class Config(C.Structure):
@@ -65,6 +66,14 @@ def _load():
         'amtfeat_pipeline_destroy': (None, [P]),
         'amtfeat_framify_hops': (C.c_int64, [C.c_int64, C.c_int, C.c_int, C.c_int]),
         'amtfeat_framify': (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, P, P]),
+        'amtfeat_resampler_create': (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(P)]),
+        'amtfeat_resampler_destroy': (None, [P]),
+        'amtfeat_resampler_out_len': (C.c_int64, [P, C.c_int64]),
+        'amtfeat_resampler_table': (C.c_int64, [P, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        'amtfeat_ingest_workspace_bytes': (C.c_size_t, [C.c_int]),
+        'amtfeat_resample': (C.c_int, [P, P, i64p, i64p, C.c_int, P, i64p, P, C.c_size_t, P]),
+        'amtfeat_to_mono': (C.c_int, [P, C.c_int64, C.c_int, P, P]),
+        'amtfeat_rms_norm': (C.c_int, [P, i64p, i64p, C.c_int, P, C.c_size_t, P]),
         'amtfeat_profile_enable': (C.c_int, [P, C.c_int]),
         'amtfeat_profile_read': (C.c_int, [P, C.c_char_p, C.c_size_t]),
     }

@@ -170,6 +170,31 @@ AMTFEAT_API int amtfeat_framify(const float *d_in, int64_t rows, int64_t num_fra
                                 float *d_out, void *stream);
 
 /*
+ * Audio ingest on the device: what tools.load_normalize_audio (amt_tools/tools/io.py:50-87) does after
+ * decoding the file -- librosa.to_mono, librosa.resample(res_type='kaiser_best' | 'kaiser_fast') (resampy's windowed-sinc
+ * interpolation) and tools.rms_norm (amt_tools/tools/utils.py:2789-2814).  A resampler owns the interpolation table of one
+ * (sr_orig, sr_new, filter) triple; device < 0 builds a host-only object (lengths / table queries, no compute).
+ * Clips are packed like amtfeat_process inputs: element offsets + lengths.  The workspace holds per-clip descriptors.
+ */
+enum { AMTFEAT_RES_KAISER_BEST = 0, AMTFEAT_RES_KAISER_FAST = 1 };
+typedef struct amtfeat_resampler amtfeat_resampler;
+AMTFEAT_API int amtfeat_resampler_create(double sr_orig, double sr_new, int filter, int device, amtfeat_resampler **out);
+AMTFEAT_API void amtfeat_resampler_destroy(amtfeat_resampler *r);
+/* int(num_samples * sr_new / sr_orig), the output length resampy allocates */
+AMTFEAT_API int64_t amtfeat_resampler_out_len(const amtfeat_resampler *r, int64_t num_samples);
+/* Copies up to `capacity` entries of the half window (scaled by the ratio when downsampling); returns its length.
+ * num_table = table samples per zero crossing, index_step = stride per input sample (either may be NULL). */
+AMTFEAT_API int64_t amtfeat_resampler_table(const amtfeat_resampler *r, double *win, int64_t capacity, int *num_table, int *index_step);
+AMTFEAT_API size_t amtfeat_ingest_workspace_bytes(int batch);
+AMTFEAT_API int amtfeat_resample(const amtfeat_resampler *r, const float *d_in, const int64_t *in_offsets, const int64_t *num_samples,
+                                 int batch, float *d_out, const int64_t *out_offsets, void *d_ws, size_t ws_bytes, void *stream);
+/* d_in is (channels, num_samples) row-major; d_out receives the channel mean */
+AMTFEAT_API int amtfeat_to_mono(const float *d_in, int64_t num_samples, int channels, float *d_out, void *stream);
+/* in place: clip / sqrt(mean(clip^2)); an all-zero (or empty) clip is left unchanged */
+AMTFEAT_API int amtfeat_rms_norm(float *d_audio, const int64_t *offsets, const int64_t *num_samples, int batch, void *d_ws,
+                                 size_t ws_bytes, void *stream);
+
+/*
  * Measurement hook (no reference counterpart): when enabled, amtfeat_process records a CUDA event pair
  * around every kernel it launches on the launching stream; amtfeat_profile_read waits for them and
  * writes {"<kernel>": {"ms": total, "launches": n}, ...} as JSON, then clears the records.

@@ -1,0 +1,125 @@
+"""
+Audio ingest: channel mean, windowed-sinc resampling and RMS normalisation -- what
+tools.load_normalize_audio (/root/reference/amt_tools/tools/io.py:50-87) does after the decoder.
+
+CPU tests pin the oracle restatement (oracle/ingest.py) with known answers and check the library's host-side table and
+length arithmetic against it; GPU tests compare the CUDA kernels with the oracle on the same seeded inputs.
+The resampler's parity is UNPINNED (resampy is not installable here): the known answers fix the scale chain only.
+"""
+import numpy as np
+import pytest
+import torch
+
+import amt_tools_b200 as ab
+from amt_tools_b200.ingest import Resampler
+from amt_tools_b200.synth import piano_like
+from oracle import ingest as oi
+
+CASES = [(44100, 22050, 'kaiser_best'), (44100, 16000, 'kaiser_best'), (16000, 22050, 'kaiser_fast'),
+         (48000, 22050, 'kaiser_fast'), (22050, 22050 * 2, 'kaiser_best')]
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize('a,b,f', CASES)
+def test_host_table_and_lengths_match_oracle(a, b, f):
+    r = Resampler(a, b, f, host_only=True)
+    win, num_table, step = r.table()
+    owin, onum, _ = oi.sinc_window(*oi.FILTERS[f])
+    ratio = float(b) / a
+    if ratio < 1:
+        owin = ratio * owin
+    assert num_table == onum == 512 and step == int(min(1.0, ratio) * onum)
+    assert win.shape == owin.shape and np.abs(win - owin).max() < 1e-14
+    for n in (0, 1, 2, 441, 44100, 44101, 5292000, 10 ** 9 + 7):
+        assert r.out_len(n) == int(n * ratio)
+
+
+def test_unknown_filter_and_bad_rates_raise():
+    with pytest.raises(ValueError):
+        Resampler(44100, 22050, 'soxr_hq', host_only=True)
+    with pytest.raises(ValueError):
+        Resampler(0, 22050, host_only=True)
+    with pytest.raises(ValueError):
+        Resampler(44100 * 1024, 1, host_only=True)   # table stride int(scale * 512) would be 0
+
+
+@pytest.mark.parametrize('a,b,f,tol', [(44100, 22050, 'kaiser_best', 1e-6), (16000, 22050, 'kaiser_fast', 2e-4),
+                                        (44100, 16000, 'kaiser_best', 4e-3), (48000, 22050, 'kaiser_fast', 1e-3)])
+def test_oracle_known_answers(a, b, f, tol):
+    # A constant stays a constant and an in-band sinusoid stays the same sinusoid at the new rate (away from the ends).
+    # Non-dyadic ratios carry resampy's table-stride truncation (int(scale * 512)): a gain error of up to ~3e-3.
+    n = 6000
+    y = oi.resample(np.ones(n, dtype=np.float32), a, b, f)
+    m = len(y)
+    assert m == int(n * b / a)
+    assert np.abs(y[m // 4:3 * m // 4] - 1).max() < tol
+    x = np.sin(2 * np.pi * 1000.0 * np.arange(n) / a).astype(np.float32)
+    y = oi.resample(x, a, b, f)
+    want = np.sin(2 * np.pi * 1000.0 * np.arange(m) / b)
+    assert np.abs(y - want)[m // 4:3 * m // 4].max() < tol
+
+
+def test_oracle_rms_norm_and_to_mono():
+    rs = np.random.RandomState(3)
+    x = rs.randn(1000).astype(np.float32) * 0.1
+    y = oi.rms_norm(x)
+    assert abs(np.sqrt(np.mean(y.astype(np.float64) ** 2)) - 1) < 1e-6 and y.dtype == np.float32
+    z = np.zeros(10, dtype=np.float32)
+    assert oi.rms_norm(z) is z
+    st = rs.randn(2, 100).astype(np.float32)
+    assert np.allclose(oi.to_mono(st), (st[0] + st[1]) / 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('a,b,f', CASES)
+def test_resample_matches_oracle(a, b, f):
+    x = piano_like(int(a * 0.35) + 13, a, seed=7)
+    got = ab.resample(x, a, b, f).cpu().numpy()
+    want = oi.resample(x.astype(np.float64), a, b, f)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert rel_l2(got, want) < 1e-6   # float64 weights and accumulation on both sides; one float32 rounding at the end
+
+
+@pytest.mark.gpu
+def test_resample_ragged_batch_and_edges():
+    a, b = 44100, 22050
+    clips = [piano_like(n, a, seed=20 + i) for i, n in enumerate((4000, 1, 2, 777, 12001))] + [np.zeros(0, dtype=np.float32)]
+    r = Resampler(a, b)
+    outs = r(clips)
+    assert [int(o.numel()) for o in outs] == [int(len(c) * b / a) for c in clips]
+    for c, o in zip(clips, outs):
+        if o.numel():
+            assert rel_l2(o.cpu().numpy(), oi.resample(c.astype(np.float64), a, b)) < 1e-6
+    one = r(torch.from_numpy(clips[0]).cuda())
+    assert torch.equal(one, outs[0])
+
+
+@pytest.mark.gpu
+def test_rms_norm_to_mono_and_full_ingest():
+    rs = np.random.RandomState(11)
+    stereo = (rs.randn(2, 44100) * 0.05).astype(np.float32)
+    mono = ab.to_mono(stereo).cpu().numpy()
+    assert np.abs(mono - oi.to_mono(stereo)).max() < 1e-7
+    x = piano_like(50001, 22050, seed=2) * 0.3
+    got = ab.rms_norm(x).cpu().numpy()
+    want = oi.rms_norm(x.astype(np.float32))
+    assert rel_l2(got, want) < 2e-7
+    z = torch.zeros(100, device='cuda')
+    assert torch.equal(ab.rms_norm(z), z)                         # silent audio is left alone (utils.py:2810)
+    t = torch.from_numpy(x).cuda()
+    out = ab.rms_norm(t)
+    assert out.data_ptr() != t.data_ptr() and torch.equal(t.cpu(), torch.from_numpy(x))   # the input is not modified
+    y, fs = ab.load_normalize_audio(stereo, 44100, fs=22050)
+    wy, wfs = oi.load_normalize_audio(stereo, 44100, fs=22050)
+    assert fs == wfs == 22050 and y.is_cuda and y.shape == wy.shape
+    assert rel_l2(y.cpu().numpy(), wy) < 1e-6
+    y2, fs2 = ab.load_normalize_audio(stereo[0], 44100, norm=None)
+    assert fs2 == 44100 and torch.equal(y2.cpu(), torch.from_numpy(stereo[0]))
+    # straight into a feature module, no host round trip
+    feats = ab.MelSpec(sample_rate=22050).process_audio(y)
+    assert feats.shape == (1, 229, 1 + y.numel() // 512)
+    with pytest.raises(ValueError):
+        ab.load_normalize_audio(stereo, 44100, norm=np.inf)
