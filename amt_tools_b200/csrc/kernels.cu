@@ -145,6 +145,64 @@ __device__ __forceinline__ float2 load_pair(const float *__restrict__ src, long 
     return v;
 }
 
+// One work item of the mel projection (segment form, see the kernel): the lanes take 32 consecutive segments of group
+// `grp` in lock step over the group's widest segment and accumulate FC frames starting at frame f0.
+template <int FC, int PT>
+__device__ __forceinline__ void mel_item(const float *Pbuf, float *s_U, float *s_V, const StftParams &p, int grp, int f0, int lane,
+                                         int nseg, int NC) {
+    const int sgm = grp * 32 + lane;
+    const int steps = __ldg(p.mel_gsteps + grp);
+    const float2 *ww = p.mel_ww + __ldg(p.mel_goff + grp) + lane;
+    const int k0 = sgm < nseg ? __ldg(p.mel_seg_start + sgm) : 0;
+    float u[FC], v[FC];
+#pragma unroll
+    for (int f = 0; f < FC; ++f) u[f] = v[f] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < steps; ++j) {
+        const float2 wv = __ldg(ww + j * 32);
+        const float *pp = Pbuf + min(k0 + j, NC) * PT + f0;
+#pragma unroll
+        for (int f = 0; f < FC; ++f) {
+            const float x = pp[f];
+            u[f] = fmaf(wv.x, x, u[f]);
+            v[f] = fmaf(wv.y, x, v[f]);
+        }
+    }
+    if (sgm < nseg) {
+#pragma unroll
+        for (int f = 0; f < FC; ++f) {
+            s_U[sgm * PT + f0 + f] = u[f];
+            s_V[sgm * PT + f0 + f] = v[f];
+        }
+    }
+}
+
+// Stores `rows` x TT values of a tile as T-contiguous rows, VW frames per thread and store (VW = 4 / 2 when the clip's rows
+// are 16 / 8-byte aligned; a tile starts at a multiple of 8 frames, so a vector never straddles the end of the clip).
+// `load(row, t)` fetches the raw value, `conv` maps it to the stored one; returns the thread's maximum raw value.
+template <int VW, int TT, typename LoadFn, typename ConvFn>
+__device__ __forceinline__ float store_tile(int rows, float *__restrict__ out, int T, int t0, int tid, LoadFn load, ConvFn conv) {
+    constexpr int QT = TT / VW;
+    float vmax = 0.f;
+    for (int idx = tid; idx < rows * QT; idx += kThreads) {
+        const int t = (idx % QT) * VW, r = idx / QT;
+        if (t0 + t < T) {
+            float v[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) {
+                const float x = load(r, t + j);
+                vmax = fmaxf(vmax, x);
+                v[j] = conv(x);
+            }
+            float *dst = out + (long long)r * T + t0 + t;
+            if (VW == 4) *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else if (VW == 2) *reinterpret_cast<float2 *>(dst) = make_float2(v[0], v[1]);
+            else dst[0] = v[0];
+        }
+    }
+    return vmax;
+}
+
 template <int NC, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     using L = FftLayout<NC>;
@@ -168,6 +226,8 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
     const bool overlap = p.hop <= NFFT;
     float *out = p.out + cm->out_off;
     float vmax = 0.f;
+    const int vw = ((T & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 4
+                   : ((T & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) ? 2 : 1;
 
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i < NC / 2; i += kThreads) s_tw2[i] = p.tw2[i];
@@ -248,57 +308,28 @@ __global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
             // of filter seg(k) and the falling slope of filter seg(k) - 1, so every power value is read once:
             //   U[s] = sum_{k in segment s} up_k P[k],  V[s] = sum down_k P[k],  mel[m] = U[m] + V[m + 1].
             // One thread per (segment, chunk of 8 frames); the (up, down) weights are padded lane-major per group of 32 segments.
+            // (A host-balanced schedule of (group, 2/4/8-frame chunk) items over the warps was measured: slower, the extra
+            // weight loads cost more than the imbalance the second resident CTA already hides.)
             float *s_U = Pbuf + (NC + 1) * PT, *s_V = s_U + (p.n_mels + 1) * PT;
-            const int nseg = p.n_mels + 1, ngroups = (nseg + 31) >> 5;
-            constexpr int NCHUNK = TT / 8;
-            for (int w = warp; w < ngroups * NCHUNK; w += kWarpsPerCta) {
-                const int grp = w / NCHUNK, ch = w % NCHUNK;
-                const int sgm = grp * 32 + lane;
-                const int steps = __ldg(p.mel_gsteps + grp);
-                const float2 *ww = p.mel_ww + __ldg(p.mel_goff + grp) + lane;
-                const int k0 = sgm < nseg ? __ldg(p.mel_seg_start + sgm) : 0;
-                float u[8], v[8];
-#pragma unroll
-                for (int f = 0; f < 8; ++f) u[f] = v[f] = 0.f;
-#pragma unroll 2
-                for (int j = 0; j < steps; ++j) {
-                    const float2 wv = __ldg(ww + j * 32);
-                    const float *pp = Pbuf + min(k0 + j, NC) * PT + ch * 8;
-#pragma unroll
-                    for (int f = 0; f < 8; ++f) {
-                        const float x = pp[f];
-                        u[f] = fmaf(wv.x, x, u[f]);
-                        v[f] = fmaf(wv.y, x, v[f]);
-                    }
-                }
-                if (sgm < nseg) {
-#pragma unroll
-                    for (int f = 0; f < 8; ++f) {
-                        s_U[sgm * PT + ch * 8 + f] = u[f];
-                        s_V[sgm * PT + ch * 8 + f] = v[f];
-                    }
-                }
+            const int nseg = p.n_mels + 1;
+            {
+                const int ngroups = (nseg + 31) >> 5;
+                constexpr int NCHUNK = TT / 8;
+                for (int w = warp; w < ngroups * NCHUNK; w += kWarpsPerCta)
+                    mel_item<8, PT>(Pbuf, s_U, s_V, p, w / NCHUNK, (w % NCHUNK) * 8, lane, nseg, NC);
             }
             __syncthreads();
-            const int total = p.n_mels * TT;
-            for (int idx = tid; idx < total; idx += kThreads) {
-                const int t = idx % TT, m = idx / TT;
-                if (t0 + t < T) {
-                    const float v = s_U[m * PT + t] + s_V[(m + 1) * PT + t];
-                    vmax = fmaxf(vmax, v);
-                    out[(long long)m * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : v;
-                }
-            }
+            auto load = [&](int m, int t) { return s_U[m * PT + t] + s_V[(m + 1) * PT + t]; };
+            auto conv = [&](float v) { return p.decibels ? db10(fmaxf(1e-10f, v)) : v; };
+            if (vw == 4) vmax = fmaxf(vmax, store_tile<4, TT>(p.n_mels, out, T, t0, tid, load, conv));
+            else if (vw == 2) vmax = fmaxf(vmax, store_tile<2, TT>(p.n_mels, out, T, t0, tid, load, conv));
+            else vmax = fmaxf(vmax, store_tile<1, TT>(p.n_mels, out, T, t0, tid, load, conv));
         } else {
-            constexpr int total = (NC + 1) * TT;
-            for (int idx = tid; idx < total; idx += kThreads) {
-                const int t = idx % TT, k = idx / TT;
-                if (t0 + t < T) {
-                    const float v = Pbuf[k * PT + t];
-                    vmax = fmaxf(vmax, v);
-                    out[(long long)k * T + t0 + t] = p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v);
-                }
-            }
+            auto load = [&](int k, int t) { return Pbuf[k * PT + t]; };
+            auto conv = [&](float v) { return p.decibels ? db10(fmaxf(1e-10f, v)) : sqrtf(v); };
+            if (vw == 4) vmax = fmaxf(vmax, store_tile<4, TT>(NC + 1, out, T, t0, tid, load, conv));
+            else if (vw == 2) vmax = fmaxf(vmax, store_tile<2, TT>(NC + 1, out, T, t0, tid, load, conv));
+            else vmax = fmaxf(vmax, store_tile<1, TT>(NC + 1, out, T, t0, tid, load, conv));
         }
     }
     if (p.decibels) {
