@@ -217,6 +217,36 @@ def kernel_algorithmic_bytes(mod, name, n):
     return 0
 
 
+def algorithmic_flops(mod, n):
+    """
+    SURVEY.md 8(d) flop model for ONE clip of n samples (useful, shared work): real FFT of size m = 2.5 m log2 m, window m,
+    power / magnitude 3 F, sparse projections 2 nnz (mel) / 8 nnz (complex wavelet rows, rows shared by octave-related
+    harmonics counted once), decimator as executed (fast-convolution form: three 1024-point complex transforms + the
+    spectral product per two blocks of 1024 - D outputs, ~111 flop per output sample), dB 6 F.
+    """
+    d = mod.describe()
+    T = mod.get_expected_frames(np.empty(n, dtype=np.float32))
+    F, Cn = mod.get_feature_size(), mod.get_num_channels()
+    db = 6.0 * Cn * F if mod.decibels else 0.0
+    name = mod.features_name()
+    if name in ('STFT', 'MelSpec'):
+        m = mod.n_fft
+        per = 2.5 * m * np.log2(m) + m + 3.0 * (m // 2 + 1) + db
+        if name == 'MelSpec':
+            per += 2.0 * 2.0 * (m // 2 + 1)     # every FFT bin feeds at most two triangular filters
+        return T * per
+    if name == 'SignalPower':
+        return 2.0 * n + T * db
+    if 'items' in d:
+        fft = sum(2.5 * it['n_fft'] * np.log2(it['n_fft']) + 3.0 * (it['kmax'] - it['kmin'] + 1) for it in d['items'])
+        uniq = sum(it['unique_rows'] for it in d['items']) / max(1, sum(it['rows'] for it in d['items']))
+        proj = 8.0 * d['basis_nnz'] * uniq
+        dec_out = sum(int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
+        dec = dec_out * (111.0 if d.get('decimator') == 'fft' else 2.0 * d['decim_taps'])
+        return T * (fft + proj + db) + dec
+    return 0.0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -422,7 +452,7 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['traffic_bytes_per_launch']
-        ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256>(CqtParams)',
+        ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512, 1>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256, 1>(CqtParams)',
                     'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
         if B == default_batch:
             traffic = tj.get(args.workload, {}).get(ncu_name)
@@ -440,6 +470,16 @@ def run_ours(args):
     hbm_floor_ms = (step_bytes + 2 * out_bytes) / (hbm_peak * 1e9) * 1e3
     roofline['step_hbm_floor_ms'] = hbm_floor_ms
     roofline['step_frac_of_hbm_floor'] = hbm_floor_ms / (ms_total / args.steps)
+    # the relevant compute roofline (every configuration is FP32-bound): algorithmic flops of the step over
+    # the FP32 FMA peak of the part at the SM clock observed during the run
+    step_flops = sum(B * algorithmic_flops(m, n) for m, n in zip(mods, n_per))
+    sm_mhz = clocks.get('sm_mhz') or clocks.get('sm_max_mhz') or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_ach = step_flops / (ms_total / args.steps * 1e-3) / 1e12
+    roofline['fp32'] = {'achieved': fp32_ach, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': fp32_ach / fp32_peak,
+                        'flops_per_step': step_flops,
+                        'model': 'SURVEY.md 8(d) algorithmic flops (FFT 2.5 n log2 n, sparse projections, decimator as '
+                                 'executed); peak = 148 SMs x 128 FMA lanes x 2 x %.0f MHz' % sm_mhz}
 
     cpu = None
     if not args.no_cpu:
