@@ -592,50 +592,54 @@ __global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFf
     float *dst = p.ladder + cm->lvl_off[p.level_out];
     float2 *scr = s_scr + warp * WP2, *cdA = s_cd + warp * kDfCd;
 
-    auto forward = [&](long long m0) {
-        const long long base = 2 * m0 - p.D;               // even: D is even
-        const bool interior = base >= 0 && base + 2048 <= len_in;
-        warp_fft_unit<1024>(scr, s_tw1, lane, [&](int, int n) {
-            const long long i = base + 2 * n;
-            if (interior) return __ldg(reinterpret_cast<const float2 *>(src + i));
-            float2 v;
-            v.x = (i >= 0 && i < len_in) ? __ldg(src + i) : 0.f;
-            v.y = (i + 1 >= 0 && i + 1 < len_in) ? __ldg(src + i + 1) : 0.f;
-            return v;
-        });
-    };
-
-    float2 cd[17];
-    forward(mA);
-    dec_fold(scr, p, lane, cd);
-#pragma unroll
-    for (int j = 0; j < 17; ++j)
-        if (lane + 32 * j <= 512) cdA[lane + 32 * j] = cd[j];
-    __syncwarp();
+    // The three transforms (forward of block A, forward of block B, inverse of both) run through ONE copy of the FFT
+    // code: the kernel is a single pass over straight-line code, so on the short deep ladder levels its time is
+    // instruction-fetch latency, and a third of the code means a third of the cold misses.
     const bool haveB = mB < len_out;
-    if (haveB) {
-        forward(mB);
-        dec_fold(scr, p, lane, cd);
-    } else {
+    float2 cd[17];
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+        if (ph == 1 && !haveB) {
 #pragma unroll
-        for (int j = 0; j < 17; ++j) cd[j] = make_float2(0.f, 0.f);
-    }
-    __syncwarp();
-    // conj(S) in the padded [n1][n2] layout the transform's first pass reads and overwrites in place
+            for (int j = 0; j < 17; ++j) cd[j] = make_float2(0.f, 0.f);
+        } else {
+            const long long base = 2 * (ph == 0 ? mA : mB) - p.D;               // even: D is even
+            const bool interior = base >= 0 && base + 2048 <= len_in;
+            warp_fft_unit<1024>(scr, s_tw1, lane, [&](int, int n) {
+                if (ph == 2) return scr[(n >> 5) * 33 + (n & 31)];
+                const long long i = base + 2 * n;
+                if (interior) return __ldg(reinterpret_cast<const float2 *>(src + i));
+                float2 v;
+                v.x = (i >= 0 && i < len_in) ? __ldg(src + i) : 0.f;
+                v.y = (i + 1 >= 0 && i + 1 < len_in) ? __ldg(src + i + 1) : 0.f;
+                return v;
+            });
+            if (ph == 2) break;
+            dec_fold(scr, p, lane, cd);
+        }
+        if (ph == 0) {
 #pragma unroll
-    for (int j = 0; j < 17; ++j) {
-        const int k = lane + 32 * j;
-        if (k <= 512) {
-            const float2 a = cdA[k], b = cd[j];
-            scr[(k >> 5) * 33 + (k & 31)] = make_float2(a.x - b.y, -a.y - b.x);
-            if (k >= 1 && k <= 511) {
-                const int n = 1024 - k;
-                scr[(n >> 5) * 33 + (n & 31)] = make_float2(a.x + b.y, a.y - b.x);
+            for (int j = 0; j < 17; ++j)
+                if (lane + 32 * j <= 512) cdA[lane + 32 * j] = cd[j];
+            __syncwarp();
+        } else {
+            __syncwarp();
+            // conj(S) in the padded [n1][n2] layout the transform's first pass reads and overwrites in place
+#pragma unroll
+            for (int j = 0; j < 17; ++j) {
+                const int k = lane + 32 * j;
+                if (k <= 512) {
+                    const float2 a = cdA[k], b = cd[j];
+                    scr[(k >> 5) * 33 + (k & 31)] = make_float2(a.x - b.y, -a.y - b.x);
+                    if (k >= 1 && k <= 511) {
+                        const int n = 1024 - k;
+                        scr[(n >> 5) * 33 + (n & 31)] = make_float2(a.x + b.y, a.y - b.x);
+                    }
+                }
             }
+            __syncwarp();
         }
     }
-    __syncwarp();
-    warp_fft_unit<1024>(scr, s_tw1, lane, [&](int, int n) { return scr[(n >> 5) * 33 + (n & 31)]; });
     // scr[n] = conj(ydA[n] + i ydB[n])
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
