@@ -30,6 +30,9 @@
 #ifndef AMT_CQT_WAVES
 #define AMT_CQT_WAVES 4        // ... while keeping at least this many waves of CTAs
 #endif
+#ifndef AMT_LADDER_OVERLAP
+#define AMT_LADDER_OVERLAP 1   // decimation ladder on a side stream underneath the projection of the shallower levels
+#endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
 #endif
@@ -1027,6 +1030,8 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
 // host: upload, workspace layout, launch
 // ------------------------------------------------------------------------------------------------
 
+static bool is_vqt_kind_cfg(int kind) { return kind == AMTFEAT_VQT || kind == AMTFEAT_HVQT; }
+
 template <typename Tp> static int upload_vec(Plan &p, const std::vector<Tp> &h, Tp **d) {
     *d = nullptr;
     if (h.empty()) return AMTFEAT_OK;
@@ -1072,6 +1077,14 @@ template <int NC> static int set_attrs() {
 
 int upload_plan(Plan &p) {
     AMT_CUDA(cudaSetDevice(p.device));
+    if (is_vqt_kind_cfg(p.cfg.kind)) {
+        // highest priority: the ladder's few CTAs take the next free SM slots instead of queueing behind a projection grid
+        int prio_lo = 0, prio_hi = 0;
+        AMT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        cudaStream_t side;
+        AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+        p.side_stream = side;
+    }
     int rc;
     if ((rc = set_attrs<1024>()) || (rc = set_attrs<512>()) || (rc = set_attrs<256>()) || (rc = set_attrs<128>()) ||
         (rc = set_attrs<64>()) || (rc = set_attrs<32>()) || (rc = set_attrs<16>()) || (rc = set_attrs<8>()) ||
@@ -1129,6 +1142,12 @@ int profile_read(const Plan &p, std::string &json) {
 }
 
 void free_plan_device(Plan &p) {
+    if (p.device >= 0 && p.side_stream) {
+        cudaSetDevice(p.device);
+        cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream));
+        cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream));
+        p.side_stream = nullptr;
+    }
     if (p.device >= 0 && !p.d_allocs.empty()) {
         cudaSetDevice(p.device);
         for (void *d : p.d_allocs) cudaFree(d);
@@ -1190,9 +1209,13 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
     int k = 0;
     if (is_vqt_kind(p)) {
         k += p.n_levels - 1;
-        int last = -1;
-        for (const CqtItem &it : p.items)
-            if (it.nfft != last) { ++k; last = it.nfft; }
+        // one projection launch per run of equal n_fft and equal ladder-depth class (see process())
+        const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
+        int last = -1, last_cls = -1;
+        for (const CqtItem &it : p.items) {
+            const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= 2 ? 1 : 2;
+            if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
+        }
     } else {
         k += 1;
     }
@@ -1348,16 +1371,30 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         AMT_CUDA(cudaGetLastError());
         return AMTFEAT_OK;
     } else {
-        // decimation ladder (levels 1 .. n_levels-1), then one launch per distinct n_fft
+        // Decimation ladder (levels 1 .. n_levels-1) on the plan's side stream, CQT launches on the caller's stream.
+        // The deep ladder levels are short and latency-bound (~20 us per launch with the GPU mostly idle), so the
+        // projection launches are cut by ladder depth -- level 0 (needs no ladder), levels 1-2, deeper -- and each class
+        // only waits for the ladder levels it reads: the ladder runs underneath the projection of the shallower levels.
         const int ntaps = (int)p.taps.size(), D = (ntaps - 1) / 2;
         const int dlen = dec_front_pad(D) + kDecTile + D + 8;
         const int dplen = ((dlen + ((dlen >> 4) << 2)) + 7) & ~3;
         const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
         const bool fast = !p.decim_hh.empty() && !p.decim_direct;
+        const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
+        cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
+        constexpr int kMidLevel = 2;                       // classes: level 0 | 1 .. kMidLevel | deeper
+        cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_all = nullptr;
+        if (overlap) {
+            AMT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            AMT_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
+            AMT_CUDA(cudaEventCreateWithFlags(&ev_all, cudaEventDisableTiming));
+            AMT_CUDA(cudaEventRecord(ev_fork, st));        // clip descriptors / cleared maxima are in place
+            AMT_CUDA(cudaStreamWaitEvent(lst, ev_fork, 0));
+        }
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
-            // (both forms have a ~28 us latency floor per launch on the short, deep levels: one warp runs three 1024-point
+            // (both forms have a ~20 us latency floor per launch on the short, deep levels: one warp runs three 1024-point
             // transforms back to back / one thread runs 16 x 389 MACs; mixing the forms per level was measured and is no faster)
             if (fast) {
                 using L = FftLayout<1024>;
@@ -1368,39 +1405,60 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 dp.level_out = l; dp.D = D; dp.M = 1024 - D;
                 const size_t fsmem = (size_t)(1024 + kDfWarps * (L::WARP_PITCH / 2) + kDfWarps * kDfCd) * sizeof(float2);
                 dim3 grid((unsigned)((len + (int64_t)kDfWarps * 2 * dp.M - 1) / ((int64_t)kDfWarps * 2 * dp.M)), batch);
-                ProfScope ps(p, "decimate_fft_kernel", st);
-                decimate_fft_kernel<<<grid, kDfThreads, fsmem, st>>>(dp);
+                ProfScope ps(p, "decimate_fft_kernel", lst);
+                decimate_fft_kernel<<<grid, kDfThreads, fsmem, lst>>>(dp);
             } else {
                 dim3 grid((unsigned)((len + kDecTile - 1) / kDecTile), batch);
-                ProfScope ps(p, "decimate_kernel", st);
-                decimate_kernel<<<grid, kThreads, dsmem, st>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
+                ProfScope ps(p, "decimate_kernel", lst);
+                decimate_kernel<<<grid, kThreads, dsmem, lst>>>(d_audio, d_ladder, d_meta, p.d_taps, ntaps, l);
             }
             AMT_CUDA(cudaGetLastError());
+            if (overlap && l == std::min(kMidLevel, p.n_levels - 1)) AMT_CUDA(cudaEventRecord(ev_mid, lst));
         }
+        if (overlap) AMT_CUDA(cudaEventRecord(ev_all, lst));
         CqtParams cp{};
         cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
         cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
         cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
         cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
-        size_t i0 = 0;
-        while (i0 < p.items.size()) {
-            size_t i1 = i0;
-            while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft) ++i1;
-            const int NC = p.items[i0].nfft / 2, cnt = (int)(i1 - i0);
-            switch (NC) {
-                case 1024: rc = launch_cqt<1024>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 512: rc = launch_cqt<512>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 256: rc = launch_cqt<256>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 128: rc = launch_cqt<128>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 64: rc = launch_cqt<64>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 32: rc = launch_cqt<32>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 16: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                case 8: rc = launch_cqt<8>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                default: rc = launch_cqt<4>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+        auto level_class = [&](int level) { return !overlap ? 0 : level == 0 ? 0 : level <= kMidLevel ? 1 : 2; };
+        for (int cls = 0; cls < (overlap ? 3 : 1); ++cls) {
+            if (cls == 1) AMT_CUDA(cudaStreamWaitEvent(st, ev_mid, 0));
+            if (cls == 2) AMT_CUDA(cudaStreamWaitEvent(st, ev_all, 0));
+            // items are sorted by n_fft, then level: a launch takes a run of equal n_fft and equal class
+            size_t i0 = 0;
+            while (i0 < p.items.size()) {
+                size_t i1 = i0;
+                while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft &&
+                       level_class(p.items[i1].level) == level_class(p.items[i0].level))
+                    ++i1;
+                if (level_class(p.items[i0].level) == cls) {
+                    const int NC = p.items[i0].nfft / 2, cnt = (int)(i1 - i0);
+                    switch (NC) {
+                        case 1024: rc = launch_cqt<1024>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 512: rc = launch_cqt<512>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 256: rc = launch_cqt<256>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 128: rc = launch_cqt<128>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 64: rc = launch_cqt<64>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 32: rc = launch_cqt<32>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 16: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        case 8: rc = launch_cqt<8>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                        default: rc = launch_cqt<4>(p, cp, (int)i0, cnt, batch, maxT, st); break;
+                    }
+                    if (rc) break;
+                }
+                i0 = i1;
             }
-            if (rc) return rc;
-            i0 = i1;
+            if (rc) break;
         }
+        if (overlap) {
+            // the caller's stream has (or, after an error, gets) a dependency on everything the side stream was given
+            if (rc) cudaStreamWaitEvent(st, ev_all, 0);
+            cudaEventDestroy(ev_fork);
+            cudaEventDestroy(ev_mid);
+            cudaEventDestroy(ev_all);
+        }
+        if (rc) return rc;
     }
     if (c.decibels) {
         int64_t maxcount = (int64_t)p.F * maxT;

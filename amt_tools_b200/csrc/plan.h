@@ -136,6 +136,7 @@ struct Plan {
     int32_t *d_mel_seg_start = nullptr;
     int32_t *d_mel_gsteps = nullptr, *d_mel_goff = nullptr;
     std::vector<void *> d_allocs;
+    void *side_stream = nullptr;               // VQT family: the decimation ladder runs here, underneath the projection launches
 
     // optional per-kernel timing (amtfeat_profile_*): CUDA event pairs recorded around every launch of
     // amtfeat_process on the launching stream.  Not thread-safe; meant for bench.py only.
