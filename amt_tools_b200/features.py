@@ -459,7 +459,26 @@ class FeatureCombo(FeatureModule):
 
     def process_audio_list(self, audio):
         audio = self._shared_upload(audio)
-        return [module.process_audio(audio) for module in self.modules]
+        dev = self.modules[0].device
+        if len(self.modules) < 2 or not torch.cuda.is_available() or not all(m.device == dev for m in self.modules) \
+                or any(m.output == 'numpy' for m in self.modules):
+            return [module.process_audio(audio) for module in self.modules]
+        # The modules are independent: each runs on its own stream (forked from / joined to the caller's stream), so a
+        # compute-bound kernel of one module runs underneath the HBM-bound dB epilogue or the short ladder levels of another.
+        streams = self.__dict__.setdefault('_streams', [torch.cuda.Stream(dev) for _ in self.modules])
+        cur = torch.cuda.current_stream(dev)
+        feats = []
+        for module, s in zip(self.modules, streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                f = module.process_audio(audio)
+            for t in (f if isinstance(f, (list, tuple)) else [f]):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)   # produced on a side stream, consumed on the caller's
+            feats.append(f)
+        for s in streams:
+            cur.wait_stream(s)
+        return feats
 
     def process_audio(self, audio):
         feats = [f for f in self.process_audio_list(audio) if f is not None]
