@@ -454,9 +454,9 @@ def run_ours(args):
         m = mods[[x.features_name() for x in mods].index(mname)]
         n = n_per[mods.index(m)]
         per_launch_ms = v['ms'] / max(v['launches'], 1)
-        bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n)
-        if k in ('decimate_kernel', 'decimate_fft_kernel'):  # one launch per ladder level: average over the levels
-            bytes_per_launch = bytes_per_launch / max(1, m.describe()['n_levels'] - 1)
+        # kernel_algorithmic_bytes covers everything this kernel name does in one step; a step may spread it over several
+        # launches (one per ladder level; one per ladder-depth class of an n_fft), so average over the launches of a step
+        bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n) / max(1.0, v['launches'] / float(args.steps))
         kern[mname + '.' + k] = {'ms_total': v['ms'], 'launches': v['launches'], 'avg_ms': per_launch_ms,
                                  'share_of_step': v['ms'] / ms_total,
                                  'algorithmic_GBps': bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
@@ -469,12 +469,17 @@ def run_ours(args):
                     'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
         if B == default_batch:
             traffic = tj.get(args.workload, {}).get(ncu_name)
+            if traffic is not None:   # the capture holds the per-step total of this kernel (it was one launch per step then)
+                traffic = traffic / max(1.0, top[1]['launches'] / float(args.steps))
     except Exception:
         pass
     roofline = {'kernel': top[0], 'bound': 'hbm', 'achieved': top[1]['algorithmic_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': (top[1]['algorithmic_GBps'] or 0.0) / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'note': 'FP32-SIMT/shared-memory bound kernel (SURVEY.md 8d): the HBM fraction is reported as required; '
-                        'see DESIGN.md for the FP32 roofline', 'kernels': kern}
+                        'roofline.fp32 is the compute roofline. Per-kernel times are CUDA-event pairs on the launching '
+                        'stream; kernels of different modules / the ladder side stream overlap, so shares add up to more '
+                        'than 1 and `traffic` is the ncu per-step total of that kernel divided by its launches per step',
+                'kernels': kern}
     step_bytes = sum(B * algorithmic_bytes(m, n) for m, n in zip(mods, n_per))
     roofline['step_algorithmic_GBps'] = step_bytes / (ms_total / args.steps * 1e-3) / 1e9
     # HBM-bound floor of the whole step (every input read once, every output written once, plus the dB epilogue's
