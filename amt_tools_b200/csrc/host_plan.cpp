@@ -399,6 +399,8 @@ static int build_vqt(Plan &p) {
     {
         const char *env = std::getenv("AMTFEAT_DECIM");
         p.decim_direct = env && std::string(env) == "direct";
+        const char *env_s = std::getenv("AMTFEAT_SLIDE");
+        p.slide_off = env_s && std::string(env_s) == "0";
         const int nt = (int)p.taps.size(), D = (nt - 1) / 2;
         if (1024 - D >= 256) {
             build_fft_tables(p, 2048);
@@ -693,7 +695,8 @@ std::string describe(const Plan &p) {
         for (size_t i = 0; i < p.items.size(); ++i) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
-              << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"unique_rows\": " << it.nuniq << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax << "}";
+              << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"unique_rows\": " << it.nuniq << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax
+              << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << "}";
         }
         o << "]";
     }

@@ -928,6 +928,268 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K1 + K5, deep ladder levels : sliding DFT (cqt_slide_kernel)
+//
+// On the deep levels of the ladder hop << n_fft (HCQT: hop 16 ... 2 against n_fft 1024), so consecutive rectangular frames
+// share all but `hop` samples and one FFT per frame recomputes almost everything.  With W = exp(-2 pi i / N) and
+// P_t[k] = W^(k t hop) the frame spectrum is  X_t[k] = conj(P_t[k]) * B_t[k],
+//     B_t[k] = sum over the frame's samples x[j] W^(k (j + N/2)),    (absolute phase: W^(k N) = 1, so a sample enters
+//     B_(t+1)[k] = B_t[k] + P_t[k] * sum_{m < hop} d_t[m] W^(k m),    and leaves with the SAME factor)
+//     d_t[m] = x[t hop + N/2 + m] - x[t hop - N/2 + m].
+// One thread owns one bin k of the item's band and walks the frames of a tile: 2 hop real-by-complex MACs with
+// register-resident twiddles + a handful of complex operations per frame instead of an N-point FFT shared by the band
+// (n_fft 1024, hop 8, 207 band bins: ~36 instructions per bin and frame).  Numerics: B is only ever ADDED to (no
+// multiplicative state), with Kahan compensation; P is re-seeded from the exact table every 32 frames; a tile starts
+// from B = 0 and a lead-in of N / hop sample groups (the first window), so errors never outlive a tile.  Every 32 frames
+// the band spectra are handed to the same blocked projection as cqt_kernel through Dbuf[k][frame].
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kSlideMaxItems = 24;          // items per launch (grid.z)
+constexpr int kSlideFL = 32;                // frames per projection chunk
+constexpr int kSlideDP = kSlideFL + 1;      // Dbuf pitch (float2)
+
+struct SlideParams {
+    const float *audio, *ladder;
+    float *out;
+    const ClipMeta *meta;
+    float *maxbuf;
+    const CqtItem *items;
+    const CqtBlock4 *blocks;
+    const float4 *weights4;
+    int C, decibels, w_off, blk_off, x_off;
+    int idx[kSlideMaxItems];
+    const float2 *tw2[kSlideMaxItems];
+};
+
+__host__ __device__ inline int slide_tile_frames(int hop) { return 4096 / hop < 1024 ? 4096 / hop : 1024; }
+
+// W_N^e from the half table tw2[k] = exp(-i pi k / NC), k = 0 .. NC (N = 2 NC)
+__device__ __forceinline__ float2 tw_full(const float2 *__restrict__ tw2, int e, int NC) {
+    e &= 2 * NC - 1;
+    if (e <= NC) return __ldg(tw2 + e);
+    const float2 w = __ldg(tw2 + 2 * NC - e);
+    return make_float2(w.x, -w.y);
+}
+
+template <int H>
+__device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &it, const float2 *__restrict__ tw2,
+                                          const ClipMeta *cm, int t0, int Tt, float *s_reg, int *s_max) {
+    constexpr int FL = kSlideFL, DP = kSlideDP, HP = (H + 1) / 2;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int N = it.nfft, NC = N >> 1, Q = N / H;
+    const int kb = it.kmax - it.kmin + 1;
+    const bool active = tid < kb;
+    const int k = it.kmin + tid;
+    const int T = cm->T;
+    float2 *Dbuf = reinterpret_cast<float2 *>(s_reg);
+    const float4 *s_w = reinterpret_cast<const float4 *>(s_reg + p.w_off);
+    const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_reg + p.blk_off);
+    float *s_x = s_reg + p.x_off;
+
+    // W^(k m), m < H, as (re, re) / (im, im) pairs of consecutive samples: one packed FFMA2 per pair and component
+    float2 wre[HP], wim[HP];
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+        const float2 w0 = tw_full(tw2, k * (2 * q), NC);
+        const float2 w1 = (2 * q + 1 < H) ? tw_full(tw2, k * (2 * q + 1), NC) : make_float2(0.f, 0.f);
+        wre[q] = make_float2(w0.x, w1.x);
+        wim[q] = make_float2(w0.y, w1.y);
+    }
+    const float2 R = tw_full(tw2, k * H, NC);
+    float2 B = make_float2(0.f, 0.f), cmp = make_float2(0.f, 0.f), P = make_float2(1.f, 0.f);
+    auto seed = [&](int t) { return tw_full(tw2, k * ((t * H) & (N - 1)), NC); };
+    // B += P * sum_m xs[m] W^(k m);  P *= W^(k H)
+    auto step = [&](const float *xs) {
+        float2 are = make_float2(0.f, 0.f), aim = make_float2(0.f, 0.f);
+        if (H >= 4) {
+#pragma unroll
+            for (int q4 = 0; q4 < H / 4; ++q4) {
+                const float4 v = *reinterpret_cast<const float4 *>(xs + 4 * q4);
+                are = ffma2(make_float2(v.x, v.y), wre[2 * q4], are);
+                aim = ffma2(make_float2(v.x, v.y), wim[2 * q4], aim);
+                are = ffma2(make_float2(v.z, v.w), wre[2 * q4 + 1], are);
+                aim = ffma2(make_float2(v.z, v.w), wim[2 * q4 + 1], aim);
+            }
+        } else if (H == 2) {
+            const float2 v = *reinterpret_cast<const float2 *>(xs);
+            are = ffma2(v, wre[0], are);
+            aim = ffma2(v, wim[0], aim);
+        } else {
+            are.x = xs[0] * wre[0].x;
+            aim.x = xs[0] * wim[0].x;
+        }
+        const float dx = are.x + are.y, dy = aim.x + aim.y;
+        const float tx = fmaf(P.x, dx, -P.y * dy), ty = fmaf(P.x, dy, P.y * dx);
+        const float yx = tx - cmp.x, yy = ty - cmp.y;          // Kahan-compensated B += (tx, ty)
+        const float nx = B.x + yx, ny = B.y + yy;
+        cmp.x = (nx - B.x) - yx;
+        cmp.y = (ny - B.y) - yy;
+        B.x = nx;
+        B.y = ny;
+        P = cmul(P, R);
+    };
+
+    // lead-in: the first window of the tile enters sample group by sample group
+    if (active) {
+#pragma unroll 2
+        for (int u = 0; u < Q; ++u) {
+            if ((u & 31) == 0) P = seed(t0 - Q + u);
+            step(s_x + u * H);
+        }
+    }
+    __syncthreads();
+    // in place x[i] <- x[i + N] - x[i]  (entering minus leaving sample), one residue class mod N per thread
+    for (int r = tid; r < N; r += NT) {
+        float prev = s_x[r];
+        for (int i = r; i < Tt * H; i += N) {
+            const float nxt = s_x[i + N];
+            s_x[i] = nxt - prev;
+            prev = nxt;
+        }
+    }
+    __syncthreads();
+
+    float *out = p.out + cm->out_off;
+    const int sub = tid / FL, lt = tid % FL, NSUB = NT / FL;
+    for (int c0 = 0; c0 < Tt && t0 + c0 < T; c0 += FL) {
+        if (active) {
+            P = seed(t0 + c0);
+            float2 *dp = Dbuf + tid * DP;
+#pragma unroll 4
+            for (int f = 0; f < FL; ++f) {
+                dp[f] = make_float2(fmaf(P.x, B.x, P.y * B.y), fmaf(P.x, B.y, -P.y * B.x));   // conj(P) * B
+                step(s_x + (c0 + f) * H);
+            }
+        }
+        __syncthreads();
+        // projection of the chunk: same blocked form as cqt_kernel (lanes along frames, 4 rows per block, packed row pairs)
+        for (int w = sub; w < it.nblk; w += NSUB) {
+            const CqtBlock4 *bl = s_blk + w;
+            const int steps = bl->steps;
+            const float4 *wt = s_w + (bl->woff - it.woff0);
+            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + lt;
+            float2 a0, a1, a2, a3;
+#if AMT_PROJ_PACKED
+            const float2 z2 = make_float2(0.f, 0.f);
+            float2 re01 = z2, ng01 = z2, ia01 = z2, ib01 = z2, re23 = z2, ng23 = z2, ia23 = z2, ib23 = z2;
+#pragma unroll 4
+            for (int s = 0; s < steps; ++s) {
+                const float2 d = Dp[s * DP];
+                const float4 wa = wt[2 * s], wb = wt[2 * s + 1];
+                const float2 dxx = make_float2(d.x, d.x), dyy = make_float2(d.y, d.y);
+                re01 = ffma2(make_float2(wa.x, wa.y), dxx, re01);
+                ng01 = ffma2(make_float2(wa.z, wa.w), dyy, ng01);
+                ia01 = ffma2(make_float2(wa.x, wa.y), dyy, ia01);
+                ib01 = ffma2(make_float2(wa.z, wa.w), dxx, ib01);
+                re23 = ffma2(make_float2(wb.x, wb.y), dxx, re23);
+                ng23 = ffma2(make_float2(wb.z, wb.w), dyy, ng23);
+                ia23 = ffma2(make_float2(wb.x, wb.y), dyy, ia23);
+                ib23 = ffma2(make_float2(wb.z, wb.w), dxx, ib23);
+            }
+            a0 = make_float2(re01.x - ng01.x, ia01.x + ib01.x); a1 = make_float2(re01.y - ng01.y, ia01.y + ib01.y);
+            a2 = make_float2(re23.x - ng23.x, ia23.x + ib23.x); a3 = make_float2(re23.y - ng23.y, ia23.y + ib23.y);
+#else
+            a0 = a1 = a2 = a3 = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int s = 0; s < steps; ++s) {
+                const float2 d = Dp[s * DP];
+                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
+                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
+                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
+                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
+                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
+                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
+                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
+                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
+                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
+            }
+#endif
+            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
+                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
+            const int t = t0 + c0 + lt;
+            const bool live = t < T;
+            if (live) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float v = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
+#pragma unroll
+                    for (int d = 0; d < kMaxDst; ++d) {
+                        const int off = bl->off[d][r];
+                        if (off < 0) break;
+                        out[(long long)off * T + t] = v;
+                    }
+                }
+            }
+            if (p.decibels) {
+                float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
+                int have = s_max[bl->chan[0]];
+                for (int d = 1; d < bl->ndst; ++d) have = min(have, s_max[bl->chan[d]]);
+                if (__any_sync(0xffffffffu, __float_as_int(vmax) > have)) {
+                    vmax = warp_max(vmax);
+                    if (lt == 0)
+                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) cqt_slide_kernel(const SlideParams p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const CqtItem it = p.items[p.idx[blockIdx.z]];
+    const float2 *tw2 = p.tw2[blockIdx.z];
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int T = cm->T, Tt = slide_tile_frames(it.hop);
+    const int t0 = blockIdx.x * Tt;
+    if (t0 >= T) return;
+    if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
+    {
+        // the tile's samples [t0 hop - N/2, (t0 + Tt) hop + N/2), zero outside the level signal (16-byte cp.async with zero
+        // fill: the start is a multiple of 4 samples), and the item's weights and block descriptors
+        const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
+        const long long len = cm->lvl_len[it.level];
+        const long long j0 = (long long)t0 * it.hop - it.nfft / 2;
+        const int nvec = (Tt * it.hop + it.nfft) >> 2;
+        float *s_x = smem + p.x_off;
+        for (int i = tid; i < nvec; i += NT) {
+            const long long g = j0 + 4ll * i;
+            int valid = 0;
+            if (g >= 0 && g < len) valid = (int)(len - g < 4 ? len - g : 4) * 4;
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_x + 4 * i));
+            const float *gp = src + (valid ? g : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(valid) : "memory");
+        }
+        float4 *s_w = reinterpret_cast<float4 *>(smem + p.w_off);
+        const float4 *wsrc = p.weights4 + it.woff0;
+        for (int i = tid; i < it.wcount; i += NT) {
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_w + i));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(wsrc + i) : "memory");
+        }
+        float4 *s_b = reinterpret_cast<float4 *>(smem + p.blk_off);
+        const float4 *bsrc = reinterpret_cast<const float4 *>(p.blocks + it.blk0);
+        const int n16 = it.nblk * (int)(sizeof(CqtBlock4) / 16);
+        for (int i = tid; i < n16; i += NT) {
+            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(s_b + i));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(bsrc + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    switch (it.hop) {
+        case 16: slide_run<16>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+        case 8: slide_run<8>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+        case 4: slide_run<4>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+        case 2: slide_run<2>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+        default: slide_run<1>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+    }
+    if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
+}
+
 // Fallback for tiny transforms (n_fft <= 64: the lowest octaves of a VQT with a large gamma): one thread per
 // (row, chunk of 8 frames) on the per-row tables.  Negligible share of any workload.
 template <int NC>
@@ -1092,6 +1354,7 @@ int upload_plan(Plan &p) {
         return rc;
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(cqt_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
     if ((rc = upload_vec(p, p.mel_cnt, &p.d_mel_cnt))) return rc;
@@ -1211,11 +1474,13 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
         k += p.n_levels - 1;
         // one projection launch per run of equal n_fft and equal ladder-depth class (see process())
         const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
-        int last = -1, last_cls = -1;
+        int last = -1, last_cls = -1, nslide = 0;
         for (const CqtItem &it : p.items) {
+            if (!p.slide_off && is_slide_item(it)) { ++nslide; last = -1; continue; }
             const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= 2 ? 1 : 2;
             if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
         }
+        k += (nslide + kSlideMaxItems - 1) / kSlideMaxItems;
     } else {
         k += 1;
     }
@@ -1302,6 +1567,39 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     return AMTFEAT_OK;
 }
 
+// Sliding-DFT launch over the items `idx` (all of them pass is_slide_item).
+static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<int> &idx, int batch, int maxT, cudaStream_t st) {
+    for (size_t i0 = 0; i0 < idx.size(); i0 += kSlideMaxItems) {
+        const int cnt = (int)std::min<size_t>(kSlideMaxItems, idx.size() - i0);
+        SlideParams sp{};
+        sp.audio = cp.audio; sp.ladder = cp.ladder; sp.out = cp.out; sp.meta = cp.meta; sp.maxbuf = cp.maxbuf;
+        sp.items = p.d_items; sp.blocks = cp.blocks; sp.weights4 = cp.weights4; sp.C = cp.C; sp.decibels = cp.decibels;
+        int maxkb = 0, maxw = 0, maxblk = 0, maxx = 0, tiles = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const CqtItem &it = p.items[idx[i0 + i]];
+            sp.idx[i] = idx[i0 + i];
+            sp.tw2[i] = reinterpret_cast<const float2 *>(p.fft.at(it.nfft / 2).d_tw2);
+            const int Tt = slide_tile_frames(it.hop);
+            maxkb = std::max(maxkb, it.kmax - it.kmin + 1);
+            maxw = std::max(maxw, it.wcount);
+            maxblk = std::max(maxblk, it.nblk);
+            maxx = std::max(maxx, Tt * it.hop + it.nfft);
+            tiles = std::max(tiles, (maxT + Tt - 1) / Tt);
+        }
+        const int threads = (maxkb + 31) / 32 * 32;
+        sp.w_off = (maxkb * kSlideDP * 2 + 3) / 4 * 4;
+        sp.blk_off = sp.w_off + maxw * 4;
+        sp.x_off = (sp.blk_off + maxblk * (int)(sizeof(CqtBlock4) / 4) + 3) / 4 * 4;
+        const size_t smem = (size_t)(sp.x_off + maxx + 8) * sizeof(float);
+        if (smem > 226 * 1024) { set_error("sliding-DFT tile does not fit in shared memory"); return AMTFEAT_ERR_INVALID; }
+        dim3 grid(tiles, batch, cnt);
+        ProfScope ps(p, "cqt_slide_kernel", st);
+        cqt_slide_kernel<<<grid, threads, smem, st>>>(sp);
+        AMT_CUDA(cudaGetLastError());
+    }
+    return AMTFEAT_OK;
+}
+
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
             int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream) {
     if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
@@ -1384,11 +1682,20 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
         cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
         constexpr int kMidLevel = 2;                       // classes: level 0 | 1 .. kMidLevel | deeper
-        cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_all = nullptr;
+        // items on the sliding-DFT kernel (deep levels) and the deepest level the FFT-per-frame launches read
+        std::vector<int> slide_idx;
+        int max_fft_level = 0;
+        for (size_t i = 0; i < p.items.size(); ++i) {
+            if (!p.slide_off && is_slide_item(p.items[i])) slide_idx.push_back((int)i);
+            else max_fft_level = std::max(max_fft_level, (int)p.items[i].level);
+        }
+        const int deep_level = std::min(p.n_levels - 1, std::max(max_fft_level, kMidLevel));
+        cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_all = nullptr, ev_side = nullptr;
         if (overlap) {
             AMT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
             AMT_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
             AMT_CUDA(cudaEventCreateWithFlags(&ev_all, cudaEventDisableTiming));
+            AMT_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
             AMT_CUDA(cudaEventRecord(ev_fork, st));        // clip descriptors / cleared maxima are in place
             AMT_CUDA(cudaStreamWaitEvent(lst, ev_fork, 0));
         }
@@ -1414,15 +1721,20 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             }
             AMT_CUDA(cudaGetLastError());
             if (overlap && l == std::min(kMidLevel, p.n_levels - 1)) AMT_CUDA(cudaEventRecord(ev_mid, lst));
+            if (overlap && l == deep_level) AMT_CUDA(cudaEventRecord(ev_all, lst));
         }
-        if (overlap) AMT_CUDA(cudaEventRecord(ev_all, lst));
         CqtParams cp{};
         cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
         cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
         cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
         cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
+        // The sliding-DFT items follow the ladder on its (high-priority) stream: their few, long-running CTAs start as soon
+        // as the deep levels exist and run underneath the FFT-per-frame launches of the shallower levels.
+        if (!slide_idx.empty()) rc = launch_slide(p, cp, slide_idx, batch, maxT, lst);
+        if (overlap) AMT_CUDA(cudaEventRecord(ev_side, lst));
         auto level_class = [&](int level) { return !overlap ? 0 : level == 0 ? 0 : level <= kMidLevel ? 1 : 2; };
-        for (int cls = 0; cls < (overlap ? 3 : 1); ++cls) {
+        auto item_class = [&](const CqtItem &it) { return (!p.slide_off && is_slide_item(it)) ? 3 : level_class(it.level); };
+        for (int cls = 0; cls < (overlap ? 3 : 1) && !rc; ++cls) {
             if (cls == 1) AMT_CUDA(cudaStreamWaitEvent(st, ev_mid, 0));
             if (cls == 2) AMT_CUDA(cudaStreamWaitEvent(st, ev_all, 0));
             // items are sorted by n_fft, then level: a launch takes a run of equal n_fft and equal class
@@ -1430,9 +1742,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             while (i0 < p.items.size()) {
                 size_t i1 = i0;
                 while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft &&
-                       level_class(p.items[i1].level) == level_class(p.items[i0].level))
+                       item_class(p.items[i1]) == item_class(p.items[i0]))
                     ++i1;
-                if (level_class(p.items[i0].level) == cls) {
+                if (item_class(p.items[i0]) == cls) {
                     const int NC = p.items[i0].nfft / 2, cnt = (int)(i1 - i0);
                     switch (NC) {
                         case 1024: rc = launch_cqt<1024>(p, cp, (int)i0, cnt, batch, maxT, st); break;
@@ -1452,11 +1764,12 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             if (rc) break;
         }
         if (overlap) {
-            // the caller's stream has (or, after an error, gets) a dependency on everything the side stream was given
-            if (rc) cudaStreamWaitEvent(st, ev_all, 0);
+            // the caller's stream gets a dependency on everything the side stream was given (ladder and sliding-DFT items)
+            cudaStreamWaitEvent(st, ev_side, 0);
             cudaEventDestroy(ev_fork);
             cudaEventDestroy(ev_mid);
             cudaEventDestroy(ev_all);
+            cudaEventDestroy(ev_side);
         }
         if (rc) return rc;
     }

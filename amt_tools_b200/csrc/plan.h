@@ -73,6 +73,14 @@ struct CqtItem {
     int32_t nuniq, pad_;        // distinct rows after merging rows shared by several harmonics
 };
 
+// Items whose hop is a small fraction of n_fft (the deep ladder levels: consecutive frames share all but `hop` samples)
+// are computed by cqt_slide_kernel -- a sliding DFT on the item's band -- instead of one FFT per frame.
+constexpr int kSlideMaxHop = 16;
+inline bool is_slide_item(const CqtItem &it) {
+    const int kb = it.kmax - it.kmin + 1;
+    return it.hop >= 1 && it.hop <= kSlideMaxHop && (it.hop & (it.hop - 1)) == 0 && it.nfft >= 128 && it.nfft / it.hop >= 16 && kb <= kThreads;
+}
+
 struct cfloat4 {
     float ar, ai, br, bi;
 };
@@ -109,6 +117,7 @@ struct Plan {
     // float32 taps.  Empty when the taps are too long for a 2048-point block (the direct kernel is used then).
     std::vector<cfloat4> decim_hh;
     bool decim_direct = false;                 // AMTFEAT_DECIM=direct forces the direct-form kernel (tests / A-B)
+    bool slide_off = false;                    // AMTFEAT_SLIDE=0 keeps every item on the FFT-per-frame kernel (tests / A-B)
     std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
     std::vector<cfloat> weights;               // per-row weights (host only)
     std::vector<CqtBlock4> blocks;
