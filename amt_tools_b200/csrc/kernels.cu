@@ -895,16 +895,18 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
             const int t = t0 + ch * FL + lt;
             const bool live = t < T;
             if (live) {
-                // rows shared by several harmonics are stored to each of them (the destination list is -1 terminated)
+                // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
+                float v[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float v = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-#pragma unroll
-                    for (int d = 0; d < kMaxDst; ++d) {
-                        const int off = bl->off[d][r];
-                        if (off < 0) break;
-                        out[(long long)off * T + t] = v;
-                    }
+                for (int r = 0; r < 4; ++r) v[r] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
+                float *ot = out + t;
+                const int ndst = bl->ndst;
+                for (int d = 0; d < ndst; ++d) {
+                    const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
+                    if (off.x >= 0) ot[(long long)off.x * T] = v[0];
+                    if (off.y >= 0) ot[(long long)off.y * T] = v[1];
+                    if (off.z >= 0) ot[(long long)off.z * T] = v[2];
+                    if (off.w >= 0) ot[(long long)off.w * T] = v[3];
                 }
             }
             if (p.decibels) {
@@ -946,7 +948,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kSlideMaxItems = 24;          // items per launch (grid.z)
-constexpr int kSlideFL = 32;                // frames per projection chunk
+#ifndef AMT_SLIDE_FL
+#define AMT_SLIDE_FL 32
+#endif
+#ifndef AMT_SLIDE_CTAS
+#define AMT_SLIDE_CTAS 2
+#endif
+constexpr int kSlideFL = AMT_SLIDE_FL;      // frames per projection chunk
 constexpr int kSlideDP = kSlideFL + 1;      // Dbuf pitch (float2)
 
 struct SlideParams {
@@ -1052,6 +1060,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
 
     float *out = p.out + cm->out_off;
     const int sub = tid / FL, lt = tid % FL, NSUB = NT / FL;
+    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << (((tid & 31) / FL) * FL));   // lanes of this frame group
     for (int c0 = 0; c0 < Tt && t0 + c0 < T; c0 += FL) {
         if (active) {
             P = seed(t0 + c0);
@@ -1110,23 +1119,27 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
             const int t = t0 + c0 + lt;
             const bool live = t < T;
             if (live) {
+                // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
+                float v[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float v = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-#pragma unroll
-                    for (int d = 0; d < kMaxDst; ++d) {
-                        const int off = bl->off[d][r];
-                        if (off < 0) break;
-                        out[(long long)off * T + t] = v;
-                    }
+                for (int r = 0; r < 4; ++r) v[r] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
+                float *ot = out + t;
+                const int ndst = bl->ndst;
+                for (int d = 0; d < ndst; ++d) {
+                    const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
+                    if (off.x >= 0) ot[(long long)off.x * T] = v[0];
+                    if (off.y >= 0) ot[(long long)off.y * T] = v[1];
+                    if (off.z >= 0) ot[(long long)off.z * T] = v[2];
+                    if (off.w >= 0) ot[(long long)off.w * T] = v[3];
                 }
             }
             if (p.decibels) {
                 float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
                 int have = s_max[bl->chan[0]];
                 for (int d = 1; d < bl->ndst; ++d) have = min(have, s_max[bl->chan[d]]);
-                if (__any_sync(0xffffffffu, __float_as_int(vmax) > have)) {
-                    vmax = warp_max(vmax);
+                if (__any_sync(gmask, __float_as_int(vmax) > have)) {
+#pragma unroll
+                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
                     if (lt == 0)
                         for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
                 }
@@ -1136,7 +1149,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) cqt_slide_kernel(const SlideParams p) {
+__global__ void __launch_bounds__(kThreads, AMT_SLIDE_CTAS) cqt_slide_kernel(const SlideParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
     const int tid = threadIdx.x, NT = blockDim.x;
