@@ -33,6 +33,12 @@
 #ifndef AMT_LADDER_OVERLAP
 #define AMT_LADDER_OVERLAP 1   // decimation ladder on a side stream underneath the projection of the shallower levels
 #endif
+#ifndef AMT_MID_LEVEL
+#define AMT_MID_LEVEL 3        // projection launches are cut by ladder depth: level 0 | 1 .. AMT_MID_LEVEL | deeper
+#endif
+#ifndef AMT_SLIDE_TILE
+#define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
+#endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
 #endif
@@ -970,7 +976,7 @@ struct SlideParams {
     const float2 *tw2[kSlideMaxItems];
 };
 
-__host__ __device__ inline int slide_tile_frames(int hop) { return 4096 / hop < 1024 ? 4096 / hop : 1024; }
+__host__ __device__ inline int slide_tile_frames(int hop) { return AMT_SLIDE_TILE / hop < 1024 ? AMT_SLIDE_TILE / hop : 1024; }
 
 // W_N^e from the half table tw2[k] = exp(-i pi k / NC), k = 0 .. NC (N = 2 NC)
 __device__ __forceinline__ float2 tw_full(const float2 *__restrict__ tw2, int e, int NC) {
@@ -1490,7 +1496,7 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
         int last = -1, last_cls = -1, nslide = 0;
         for (const CqtItem &it : p.items) {
             if (!p.slide_off && is_slide_item(it)) { ++nslide; last = -1; continue; }
-            const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= 2 ? 1 : 2;
+            const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= AMT_MID_LEVEL ? 1 : 2;
             if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
         }
         k += (nslide + kSlideMaxItems - 1) / kSlideMaxItems;
@@ -1694,7 +1700,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         const bool fast = !p.decim_hh.empty() && !p.decim_direct;
         const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
         cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
-        constexpr int kMidLevel = 2;                       // classes: level 0 | 1 .. kMidLevel | deeper
+        constexpr int kMidLevel = AMT_MID_LEVEL;           // classes: level 0 | 1 .. kMidLevel | deeper
         // items on the sliding-DFT kernel (deep levels) and the deepest level the FFT-per-frame launches read
         std::vector<int> slide_idx;
         int max_fft_level = 0;

@@ -201,11 +201,12 @@ def kernel_algorithmic_bytes(mod, name, n):
     T = mod.get_expected_frames(np.empty(n, dtype=np.float32))
     if name.startswith('stft_kernel'):
         return 4 * n + 4 * mod.get_feature_size() * T
-    if name.startswith('cqt_kernel_nfft'):
-        nfft = int(name[len('cqt_kernel_nfft'):])
+    if name.startswith('cqt_kernel_nfft') or name == 'cqt_slide_kernel':
+        # FFT-per-frame launches take the items of one n_fft that are not on the sliding-DFT kernel (deep ladder levels)
+        nfft = int(name[len('cqt_kernel_nfft'):]) if name != 'cqt_slide_kernel' else None
         total = 0
         for it in d['items']:
-            if it['n_fft'] == nfft:
+            if (nfft is None and it.get('slide')) or (it['n_fft'] == nfft and not it.get('slide')):
                 total += 4 * int(np.ceil(n / 2.0 ** it['level'])) + 4 * it['rows'] * T
         return total
     if name in ('decimate_kernel', 'decimate_fft_kernel'):
@@ -221,7 +222,7 @@ def algorithmic_flops(mod, n):
     """
     SURVEY.md 8(d) flop model for ONE clip of n samples (useful, shared work): real FFT of size m = 2.5 m log2 m, window m,
     power / magnitude 3 F, sparse projections 2 nnz (mel) / 8 nnz (complex wavelet rows, rows shared by octave-related
-    harmonics counted once), decimator as executed (fast-convolution form: three 1024-point complex transforms + the
+    harmonics counted once), sliding-DFT items (deep ladder levels) as executed, decimator as executed (fast-convolution form: three 1024-point complex transforms + the
     spectral product per two blocks of 1024 - D outputs, ~111 flop per output sample), dB 6 F.
     """
     d = mod.describe()
@@ -238,7 +239,16 @@ def algorithmic_flops(mod, n):
     if name == 'SignalPower':
         return 2.0 * n + T * db
     if 'items' in d:
-        fft = sum(2.5 * it['n_fft'] * np.log2(it['n_fft']) + 3.0 * (it['kmax'] - it['kmin'] + 1) for it in d['items'])
+        # FFT-per-frame items: the SURVEY model; sliding-DFT items (deep levels) as executed: per band bin and frame
+        # 4 hop flops for the entering / leaving samples + 44 for the phase bookkeeping, times the tile lead-in overhead
+        fft = 0.0
+        for it in d['items']:
+            kb = it['kmax_padded'] - it['kmin'] + 1
+            if it.get('slide'):
+                tile = min(1024, 4096 // it['hop'])
+                fft += kb * (4.0 * it['hop'] + 44.0) * (1.0 + (it['n_fft'] // it['hop']) / float(tile))
+            else:
+                fft += 2.5 * it['n_fft'] * np.log2(it['n_fft']) + 3.0 * (it['kmax'] - it['kmin'] + 1)
         uniq = sum(it['unique_rows'] for it in d['items']) / max(1, sum(it['rows'] for it in d['items']))
         proj = 8.0 * d['basis_nnz'] * uniq
         dec_out = sum(int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
@@ -466,6 +476,7 @@ def run_ours(args):
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['traffic_bytes_per_launch']
         ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512, 1>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256, 1>(CqtParams)',
+                    'cqt_slide_kernel': 'cqt_slide_kernel(SlideParams)',
                     'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
         if B == default_batch:
             traffic = tj.get(args.workload, {}).get(ncu_name)
@@ -496,8 +507,8 @@ def run_ours(args):
     fp32_ach = step_flops / (ms_total / args.steps * 1e-3) / 1e12
     roofline['fp32'] = {'achieved': fp32_ach, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': fp32_ach / fp32_peak,
                         'flops_per_step': step_flops,
-                        'model': 'SURVEY.md 8(d) algorithmic flops (FFT 2.5 n log2 n, sparse projections, decimator as '
-                                 'executed); peak = 148 SMs x 128 FMA lanes x 2 x %.0f MHz' % sm_mhz}
+                        'model': 'SURVEY.md 8(d) algorithmic flops (FFT 2.5 n log2 n, sparse projections; sliding-DFT items '
+                                 'and decimator as executed); peak = 148 SMs x 128 FMA lanes x 2 x %.0f MHz' % sm_mhz}
 
     cpu = None
     if not args.no_cpu:

@@ -271,3 +271,45 @@ def test_fast_convolution_decimator_matches_direct_form(monkeypatch):
         assert rel_l2(u.cpu().numpy(), v.cpu().numpy()) < 2e-6
         # lowest octave: 7 cascaded float32 stages; each form is ~5e-6 from the float64 oracle there (tools/dbg_decim.py)
         assert rel_l2(u[0, :60].cpu().numpy(), v[0, :60].cpu().numpy()) < 3e-5
+
+
+def test_sliding_dft_matches_fft_per_frame(monkeypatch):
+    # K1/K5 have two forms for an item: cqt_kernel (one FFT per frame) and, where hop << n_fft (deep ladder levels),
+    # cqt_slide_kernel (sliding DFT over the band, AMTFEAT_SLIDE=0 switches it off).  Same ladder, same basis: they must
+    # agree to float32 rounding on every clip of a ragged batch, including clips shorter than one window / one tile,
+    # tiles that end inside the clip and lengths that are not multiples of anything.
+    y = piano_like(22050 * 9 + 77, 22050, seed=91)
+    clips = [y, y[:30011], y[:1000], y[:50], y[22050:22050 * 5]]
+    cases = [
+        ('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60)),
+        ('CQT', dict(sample_rate=22050, hop_length=512, n_bins=192, bins_per_octave=24)),
+        ('VQT', dict(sample_rate=22050, hop_length=512)),
+        ('HVQT', dict(sample_rate=22050, hop_length=512, harmonics=[1, 2, 3], n_bins=72, bins_per_octave=12)),
+        ('CQT', dict(sample_rate=22050, hop_length=128, n_bins=48, bins_per_octave=12, fmin=110.0)),   # level 0..3 at hop 128..16
+    ]
+    for name, kw in cases:
+        for db in (False, True):
+            monkeypatch.delenv('AMTFEAT_SLIDE', raising=False)
+            slide = make(name, kw, db)[0]
+            flags = [it['slide'] for it in slide.describe()['items']]
+            monkeypatch.setenv('AMTFEAT_SLIDE', '0')
+            plain = make(name, kw, db)[0]
+            assert not any(it['slide'] for it in plain.describe()['items'])
+            if not any(flags):
+                continue
+            a, b = slide.process_audio(clips), plain.process_audio(clips)
+            for u, v in zip(a, b):
+                assert u.shape == v.shape
+                if u.numel() == 0:
+                    continue
+                u, v = u.cpu().numpy(), v.cpu().numpy()
+                if db:
+                    top = v > 0.25                                   # within 60 dB of the (clip, channel) maximum
+                    assert np.abs(u - v).max() * 80.0 < 2e-2
+                    assert (np.abs(u - v)[top].max() if top.any() else 0.0) * 80.0 < 2e-3
+                else:
+                    assert rel_l2(u, v) < 2e-6
+                    assert np.abs(u - v).max() <= 3e-6 * np.abs(v).max()
+    # the HCQT has sliding items: make sure the comparison above was not vacuous
+    monkeypatch.delenv('AMTFEAT_SLIDE', raising=False)
+    assert sum(it['slide'] for it in ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()['items']) == 6

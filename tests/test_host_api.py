@@ -112,6 +112,24 @@ def test_plan_description_matches_oracle_octave_plan():
     assert d1['decim_taps'] == len(ls.soxr_hq_taps(2))
 
 
+def test_sliding_dft_items_are_the_deep_levels(monkeypatch):
+    # items whose hop is a small power-of-two fraction of n_fft go to cqt_slide_kernel; AMTFEAT_SLIDE=0 keeps all of them
+    # on the FFT-per-frame kernel (the A/B switch the GPU parity test uses)
+    d = ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()
+    for it in d['items']:
+        want = it['hop'] <= 16 and it['n_fft'] >= 128 and it['n_fft'] // it['hop'] >= 16
+        assert it['slide'] == int(want), it
+    assert sorted((it['n_fft'], it['level']) for it in d['items'] if it['slide']) == \
+        [(512, 4), (512, 5), (1024, 4), (1024, 5), (1024, 6), (1024, 7)]
+    d1 = ab.CQT(22050, 512, n_bins=192, bins_per_octave=24).describe()
+    assert [it['level'] for it in d1['items'] if it['slide']] == [5, 6, 7]          # hop 16, 8, 4 against n_fft 256
+    assert not any(it['slide'] for it in ab.CQT(22050, 384, n_bins=84, bins_per_octave=12).describe()['items'][:5])
+    for it in ab.CQT(22050, 384, n_bins=84, bins_per_octave=12).describe()['items']:
+        assert it['slide'] == 0 or (it['hop'] & (it['hop'] - 1)) == 0               # hop 12, 6, 3 never slide
+    monkeypatch.setenv('AMTFEAT_SLIDE', '0')
+    assert not any(it['slide'] for it in ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()['items'])
+
+
 def test_errors_follow_the_reference():
     with pytest.raises(ValueError):      # librosa: filter cutoff above Nyquist
         ab.CQT(22050, 512, n_bins=120, bins_per_octave=12).get_expected_frames(np.zeros(100))
