@@ -294,9 +294,32 @@ def run_ours(args):
     # one stream per module: the modules of a step are independent (amtfeat_process is re-entrant on distinct stream +
     # workspace), so e.g. the compute-bound mel kernel runs underneath the HBM-bound dB epilogue of the HCQT
     mod_streams = [torch.cuda.Stream(dev) for _ in mods] if len(mods) > 1 and not args.serial_modules else None
+    # Consecutive steps are independent batches (amtfeat_process takes caller-owned output and workspace buffers), so they
+    # alternate between two sets of streams: the HBM-bound dB epilogue that ends step i runs underneath the FP32-bound
+    # kernels that start step i + 1.  --serial-steps joins every step on the current stream instead (A/B).
+    step_sets = None
+    if not args.serial_steps and not args.serial_modules:
+        step_sets = [[torch.cuda.Stream(dev) for _ in mods] for _ in range(2)]
+    step_no = [0]
+
+    def join_steps():
+        if step_sets is not None:
+            cur = torch.cuda.current_stream(dev)
+            for ss in step_sets:
+                for s in ss:
+                    cur.wait_stream(s)
 
     def step_device():
         outs = []
+        if step_sets is not None:
+            cur = torch.cuda.current_stream(dev)
+            ss = step_sets[step_no[0] % 2]
+            step_no[0] += 1
+            for m, a, s in zip(mods, dev_audio, ss):
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    outs.append(m.process_audio(a))
+            return outs
         if mod_streams is None:
             for m, a in zip(mods, dev_audio):
                 outs.append(m.process_audio(a))
@@ -324,6 +347,7 @@ def run_ours(args):
         if nwarm % 8 == 0:
             torch.cuda.synchronize()
     del outs
+    join_steps()
     barrier()
     for m in mods:
         _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 1))
@@ -332,6 +356,7 @@ def run_ours(args):
     for _ in range(args.steps):
         outs = step_device()
         del outs
+    join_steps()
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -528,7 +553,8 @@ def run_ours(args):
                    'l2': 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) exceeds the 126 MB L2'
                          % (sum(4 * B * n for n in n_per) / 1e6, (step_bytes - sum(4 * B * n for n in n_per)) / 1e6),
                    'parallelism': 'track-sharded x%d, no collective on the data path' % world,
-                   'streams': 'one CUDA stream per module, joined every step' if mod_streams else 'single stream'},
+                   'streams': ('one CUDA stream per module, consecutive steps alternate between two stream sets (joined at the end of the timed region)'
+                               if step_sets else 'one CUDA stream per module, joined every step' if mod_streams else 'single stream')},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
     }
     emit(line)
@@ -563,6 +589,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='tracks per GPU per step (0 = workload default)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--serial-modules', action='store_true', help='run the modules of a step on one stream (A/B)')
+    ap.add_argument('--serial-steps', action='store_true', help='join every step on the current stream (A/B for the step pipelining)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
