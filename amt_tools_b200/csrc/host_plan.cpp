@@ -401,6 +401,8 @@ static int build_vqt(Plan &p) {
         p.decim_direct = env && std::string(env) == "direct";
         const char *env_s = std::getenv("AMTFEAT_SLIDE");
         p.slide_off = env_s && std::string(env_s) == "0";
+        const char *env_q = std::getenv("AMTFEAT_SERIAL");
+        p.serial_launch = env_q && std::string(env_q) == "1";
         const int nt = (int)p.taps.size(), D = (nt - 1) / 2;
         if (1024 - D >= 256) {
             build_fft_tables(p, 2048);

@@ -1430,6 +1430,14 @@ void free_plan_device(Plan &p) {
         cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream));
         p.side_stream = nullptr;
     }
+    if (p.device >= 0 && p.meta_ring) {
+        cudaSetDevice(p.device);
+        for (void *&e : p.meta_events)
+            if (e) { cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(e)); cudaEventDestroy(reinterpret_cast<cudaEvent_t>(e)); e = nullptr; }
+        cudaFreeHost(p.meta_ring);
+        p.meta_ring = nullptr;
+        p.meta_slot_bytes = 0;
+    }
     if (p.device >= 0 && !p.d_allocs.empty()) {
         cudaSetDevice(p.device);
         for (void *d : p.d_allocs) cudaFree(d);
@@ -1492,7 +1500,7 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
     if (is_vqt_kind(p)) {
         k += p.n_levels - 1;
         // one projection launch per run of equal n_fft and equal ladder-depth class (see process())
-        const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
+        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream != nullptr && p.n_levels > 1;
         int last = -1, last_cls = -1, nslide = 0;
         for (const CqtItem &it : p.items) {
             if (!p.slide_off && is_slide_item(it)) { ++nslide; last = -1; continue; }
@@ -1648,7 +1656,30 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
     ClipMeta *d_meta = reinterpret_cast<ClipMeta *>(ws + w.meta_off);
     float *d_max = reinterpret_cast<float *>(ws + w.max_off);
     float *d_ladder = reinterpret_cast<float *>(ws + w.ladder_off);
-    AMT_CUDA(cudaMemcpyAsync(d_meta, metas.data(), metas.size() * sizeof(ClipMeta), cudaMemcpyHostToDevice, st));
+    {
+        // descriptors go through a pinned ring slot (truly asynchronous copy); a slot is reused once its last copy has completed
+        const size_t need = metas.size() * sizeof(ClipMeta);
+        std::lock_guard<std::mutex> lock(p.meta_mu);
+        if (need > p.meta_slot_bytes) {
+            for (void *&e : p.meta_events) {
+                if (e) AMT_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(e)));
+                else AMT_CUDA(cudaEventCreateWithFlags(reinterpret_cast<cudaEvent_t *>(&e), cudaEventDisableTiming));
+            }
+            if (p.meta_ring) cudaFreeHost(p.meta_ring);
+            p.meta_ring = nullptr;
+            p.meta_slot_bytes = 0;
+            const size_t slot = align_up(std::max<size_t>(need, 64 * 1024), 4096);
+            AMT_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&p.meta_ring), slot * Plan::kMetaSlots, cudaHostAllocDefault));
+            p.meta_slot_bytes = slot;
+        }
+        const unsigned slot = p.meta_next++ % Plan::kMetaSlots;
+        cudaEvent_t ev = reinterpret_cast<cudaEvent_t>(p.meta_events[slot]);
+        AMT_CUDA(cudaEventSynchronize(ev));
+        char *h = p.meta_ring + (size_t)slot * p.meta_slot_bytes;
+        std::memcpy(h, metas.data(), need);
+        AMT_CUDA(cudaMemcpyAsync(d_meta, h, need, cudaMemcpyHostToDevice, st));
+        AMT_CUDA(cudaEventRecord(ev, st));
+    }
     if (c.decibels) AMT_CUDA(cudaMemsetAsync(d_max, 0, (size_t)batch * p.C * sizeof(float), st));
     int rc = AMTFEAT_OK;
     int scale01 = 1;
@@ -1698,7 +1729,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
         const bool fast = !p.decim_hh.empty() && !p.decim_direct;
-        const bool overlap = AMT_LADDER_OVERLAP && p.side_stream != nullptr && p.n_levels > 1;
+        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream != nullptr && p.n_levels > 1;
         cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
         constexpr int kMidLevel = AMT_MID_LEVEL;           // classes: level 0 | 1 .. kMidLevel | deeper
         // items on the sliding-DFT kernel (deep levels) and the deepest level the FFT-per-frame launches read

@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -117,6 +118,7 @@ struct Plan {
     // float32 taps.  Empty when the taps are too long for a 2048-point block (the direct kernel is used then).
     std::vector<cfloat4> decim_hh;
     bool decim_direct = false;                 // AMTFEAT_DECIM=direct forces the direct-form kernel (tests / A-B)
+    bool serial_launch = false;                // AMTFEAT_SERIAL=1: no side stream, every launch in order on the caller's stream (isolated per-kernel timing)
     bool slide_off = false;                    // AMTFEAT_SLIDE=0 keeps every item on the FFT-per-frame kernel (tests / A-B)
     std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
     std::vector<cfloat> weights;               // per-row weights (host only)
@@ -146,6 +148,15 @@ struct Plan {
     int32_t *d_mel_gsteps = nullptr, *d_mel_goff = nullptr;
     std::vector<void *> d_allocs;
     void *side_stream = nullptr;               // VQT family: the decimation ladder runs here, underneath the projection launches
+
+    // Pinned staging ring for the per-call clip descriptors: a cudaMemcpyAsync from pageable memory makes the host wait for
+    // the stream to drain first, which would serialise a caller that queues an upload and then amtfeat_process behind it.
+    static constexpr int kMetaSlots = 8;
+    mutable std::mutex meta_mu;
+    mutable char *meta_ring = nullptr;
+    mutable size_t meta_slot_bytes = 0;
+    mutable unsigned meta_next = 0;
+    mutable void *meta_events[kMetaSlots] = {};
 
     // optional per-kernel timing (amtfeat_profile_*): CUDA event pairs recorded around every launch of
     // amtfeat_process on the launching stream.  Not thread-safe; meant for bench.py only.

@@ -360,13 +360,42 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    prof = {}
-    for m in mods:
-        buf = C.create_string_buffer(1 << 16)
-        _lib.check(_lib.lib.amtfeat_profile_read(m._dev_plan.handle, buf, len(buf)))
-        _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 0))
-        for k, v in json.loads(buf.value.decode()).items():
-            prof[(m.features_name(), k)] = v
+    def read_profile(modules):
+        res = {}
+        for m in modules:
+            buf = C.create_string_buffer(1 << 16)
+            _lib.check(_lib.lib.amtfeat_profile_read(m._dev_plan.handle, buf, len(buf)))
+            _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 0))
+            for k, v in json.loads(buf.value.decode()).items():
+                res[(m.features_name(), k)] = v
+        return res
+
+    prof_overlapped = read_profile(mods)
+    # Isolated per-kernel durations for the roofline: in the timed region the kernels of different modules, of the ladder side
+    # stream and of consecutive steps share the SMs, so an event pair around one launch also measures its neighbours.  A
+    # second set of plans created with AMTFEAT_SERIAL=1 (no side stream) runs the same steps one launch at a time.
+    os.environ['AMTFEAT_SERIAL'] = '1'
+    smods = [getattr(ab, name)(device=dev, **kw) for (name, kw, sr) in spec]
+    for m, a in zip(smods, dev_audio):
+        m.process_audio(a)                      # builds the plan while the switch is set
+    del os.environ['AMTFEAT_SERIAL']
+    for _ in range(2):
+        for m, a in zip(smods, dev_audio):
+            m.process_audio(a)
+    torch.cuda.synchronize()
+    for m in smods:
+        _lib.check(_lib.lib.amtfeat_profile_enable(m._dev_plan.handle, 1))
+    iso_steps = max(3, min(args.steps, 10))
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(iso_steps):
+        for m, a in zip(smods, dev_audio):
+            m.process_audio(a)
+    i1.record()
+    torch.cuda.synchronize()
+    iso_ms_per_step = i0.elapsed_time(i1) / iso_steps
+    prof = read_profile(smods)
+    del smods
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
@@ -491,11 +520,13 @@ def run_ours(args):
         per_launch_ms = v['ms'] / max(v['launches'], 1)
         # kernel_algorithmic_bytes covers everything this kernel name does in one step; a step may spread it over several
         # launches (one per ladder level; one per ladder-depth class of an n_fft), so average over the launches of a step
-        bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n) / max(1.0, v['launches'] / float(args.steps))
-        kern[mname + '.' + k] = {'ms_total': v['ms'], 'launches': v['launches'], 'avg_ms': per_launch_ms,
-                                 'share_of_step': v['ms'] / ms_total,
+        bytes_per_launch = B * kernel_algorithmic_bytes(m, k, n) / max(1.0, v['launches'] / float(iso_steps))
+        ov = prof_overlapped.get((mname, k))
+        kern[mname + '.' + k] = {'ms_per_step': v['ms'] / iso_steps, 'launches_per_step': v['launches'] / float(iso_steps),
+                                 'avg_ms': per_launch_ms, 'share_of_isolated_step': v['ms'] / (iso_ms_per_step * iso_steps),
+                                 'ms_per_step_in_timed_region': (ov['ms'] / args.steps) if ov else None,
                                  'algorithmic_GBps': bytes_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else None}
-    top = max(kern.items(), key=lambda kv: kv[1]['ms_total'])
+    top = max(kern.items(), key=lambda kv: kv[1]['ms_per_step'])
     # measured DRAM traffic per launch of that kernel (ncu --set full capture of this workload, profiles/r01_traffic.json)
     traffic = None
     try:
@@ -506,16 +537,18 @@ def run_ours(args):
         if B == default_batch:
             traffic = tj.get(args.workload, {}).get(ncu_name)
             if traffic is not None:   # the capture holds the per-step total of this kernel (it was one launch per step then)
-                traffic = traffic / max(1.0, top[1]['launches'] / float(args.steps))
+                traffic = traffic / max(1.0, top[1]['launches_per_step'])
     except Exception:
         pass
     roofline = {'kernel': top[0], 'bound': 'hbm', 'achieved': top[1]['algorithmic_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': (top[1]['algorithmic_GBps'] or 0.0) / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'note': 'FP32-SIMT/shared-memory bound kernel (SURVEY.md 8d): the HBM fraction is reported as required; '
-                        'roofline.fp32 is the compute roofline. Per-kernel times are CUDA-event pairs on the launching '
-                        'stream; kernels of different modules / the ladder side stream overlap, so shares add up to more '
-                        'than 1 and `traffic` is the ncu per-step total of that kernel divided by its launches per step',
-                'kernels': kern}
+                        'roofline.fp32 is the compute roofline. Per-kernel durations are CUDA-event pairs from an isolated pass '
+                        '(same steps, plans created with AMTFEAT_SERIAL=1: one launch at a time on one stream); in the timed '
+                        'region the same kernels overlap across modules, the ladder side stream and consecutive steps '
+                        '(ms_per_step_in_timed_region). `traffic` is the ncu per-step DRAM total of that kernel divided by '
+                        'its launches per step',
+                'isolated_ms_per_step': iso_ms_per_step, 'kernels': kern}
     step_bytes = sum(B * algorithmic_bytes(m, n) for m, n in zip(mods, n_per))
     roofline['step_algorithmic_GBps'] = step_bytes / (ms_total / args.steps * 1e-3) / 1e9
     # HBM-bound floor of the whole step (every input read once, every output written once, plus the dB epilogue's
