@@ -285,7 +285,8 @@ def test_sliding_dft_matches_fft_per_frame(monkeypatch):
         ('CQT', dict(sample_rate=22050, hop_length=512, n_bins=192, bins_per_octave=24)),
         ('VQT', dict(sample_rate=22050, hop_length=512)),
         ('HVQT', dict(sample_rate=22050, hop_length=512, harmonics=[1, 2, 3], n_bins=72, bins_per_octave=12)),
-        ('CQT', dict(sample_rate=22050, hop_length=128, n_bins=48, bins_per_octave=12, fmin=110.0)),   # level 0..3 at hop 128..16
+        ('CQT', dict(sample_rate=22050, hop_length=128, n_bins=48, bins_per_octave=12, fmin=110.0)),   # hop 16 and 8 on levels 3, 4
+        ('CQT', dict(sample_rate=22050, hop_length=128, n_bins=96, bins_per_octave=12)),               # 8 octaves: hop 8, 4, 2 and 1
     ]
     for name, kw in cases:
         for db in (False, True):
