@@ -1365,8 +1365,6 @@ int upload_plan(Plan &p) {
         cudaStream_t side;
         AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
         p.side_stream = side;
-        AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
-        p.side_stream2 = side;
     }
     int rc;
     if ((rc = set_attrs<1024>()) || (rc = set_attrs<512>()) || (rc = set_attrs<256>()) || (rc = set_attrs<128>()) ||
@@ -1431,11 +1429,6 @@ void free_plan_device(Plan &p) {
         cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream));
         cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream));
         p.side_stream = nullptr;
-        if (p.side_stream2) {
-            cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream2));
-            cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream2));
-            p.side_stream2 = nullptr;
-        }
     }
     if (p.device >= 0 && p.meta_ring) {
         cudaSetDevice(p.device);
@@ -1737,15 +1730,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         int64_t len = maxn;
         const bool fast = !p.decim_hh.empty() && !p.decim_direct;
         const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream != nullptr && p.n_levels > 1;
-#ifndef AMT_SIDE_ALTERNATE
-#define AMT_SIDE_ALTERNATE 1
-#endif
-        unsigned side_sel = 0;
-        if (overlap && AMT_SIDE_ALTERNATE && p.side_stream2) {
-            std::lock_guard<std::mutex> lock(p.meta_mu);
-            side_sel = p.side_next++ & 1u;
-        }
-        cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(side_sel ? p.side_stream2 : p.side_stream) : st;
+        cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
         constexpr int kMidLevel = AMT_MID_LEVEL;           // classes: level 0 | 1 .. kMidLevel | deeper
         // items on the sliding-DFT kernel (deep levels) and the deepest level the FFT-per-frame launches read
         std::vector<int> slide_idx;

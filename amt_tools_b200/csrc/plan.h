@@ -148,8 +148,6 @@ struct Plan {
     int32_t *d_mel_gsteps = nullptr, *d_mel_goff = nullptr;
     std::vector<void *> d_allocs;
     void *side_stream = nullptr;               // VQT family: the decimation ladder runs here, underneath the projection launches
-    void *side_stream2 = nullptr;              // ... consecutive calls alternate between two, so the ladder of call i + 1 does not
-    mutable unsigned side_next = 0;            //     queue behind the sliding-DFT kernel of call i
 
     // Pinned staging ring for the per-call clip descriptors: a cudaMemcpyAsync from pageable memory makes the host wait for
     // the stream to drain first, which would serialise a caller that queues an upload and then amtfeat_process behind it.
