@@ -1,0 +1,9 @@
+import numpy as np, torch, sys
+sys.path.insert(0, '.')
+import amt_tools_b200 as ab
+from amt_tools_b200.synth import piano_like
+y = piano_like(22050 * 3 + 77, 22050, seed=1)
+for m in (ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60), ab.CQT(22050, 128, n_bins=96, bins_per_octave=12), ab.MelSpec(), ab.VQT(22050, 512)):
+    out = m.process_audio([y, y[:20011], y[:700]])
+    torch.cuda.synchronize()
+    print(type(m).__name__, [tuple(o.shape) for o in out], float(out[0].max()))
