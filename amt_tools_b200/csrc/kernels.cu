@@ -39,6 +39,9 @@
 #ifndef AMT_SLIDE_TILE
 #define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
 #endif
+#ifndef AMT_PROJ_FPL
+#define AMT_PROJ_FPL 2         // frames per lane in the blocked projection (2: one 16-byte load feeds two frames, 8-byte stores)
+#endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
 #endif
@@ -666,6 +669,87 @@ __global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFf
 // K1 + K5 : CQT / VQT / HCQT response of one (ladder level, n_fft) item
 // ------------------------------------------------------------------------------------------------
 
+#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
+constexpr int kDbufPad = 2;    // even Dbuf pitch: the two frames of a lane are one aligned 16-byte load
+// Projection of one block of 4 rows for the TWO consecutive frames (t, t + 1) this lane owns: every step is one 16-byte load of
+// the band spectra of both frames + the block's two warp-uniform weight vectors feeding 16 packed FFMA2; |.|^2 / L -> dB or
+// magnitude -> 8-byte stores (vec2: the clip's rows are 8-byte aligned and T is even) + lazy per-(clip, channel) maximum.
+__device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4 *wt, const float2 *Dp, int DP, float *out, int T, int t,
+                                               int decibels, int *s_max, unsigned gmask, int glanes, bool leader, bool vec2) {
+    const int steps = bl->steps;
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 rA01 = z2, nA01 = z2, iA01 = z2, jA01 = z2, rA23 = z2, nA23 = z2, iA23 = z2, jA23 = z2;
+    float2 rB01 = z2, nB01 = z2, iB01 = z2, jB01 = z2, rB23 = z2, nB23 = z2, iB23 = z2, jB23 = z2;
+#pragma unroll 2
+    for (int s = 0; s < steps; ++s) {
+        const float4 dd = *reinterpret_cast<const float4 *>(Dp + s * DP);
+        const float4 wa = wt[2 * s], wb = wt[2 * s + 1];
+        const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+        const float2 ax = make_float2(dd.x, dd.x), ay = make_float2(dd.y, dd.y), bx = make_float2(dd.z, dd.z), by = make_float2(dd.w, dd.w);
+        rA01 = ffma2(w0, ax, rA01); nA01 = ffma2(w1, ay, nA01); iA01 = ffma2(w0, ay, iA01); jA01 = ffma2(w1, ax, jA01);
+        rA23 = ffma2(w2, ax, rA23); nA23 = ffma2(w3, ay, nA23); iA23 = ffma2(w2, ay, iA23); jA23 = ffma2(w3, ax, jA23);
+        rB01 = ffma2(w0, bx, rB01); nB01 = ffma2(w1, by, nB01); iB01 = ffma2(w0, by, iB01); jB01 = ffma2(w1, bx, jB01);
+        rB23 = ffma2(w2, bx, rB23); nB23 = ffma2(w3, by, nB23); iB23 = ffma2(w2, by, iB23); jB23 = ffma2(w3, bx, jB23);
+    }
+    const float4 inv = *reinterpret_cast<const float4 *>(bl->inv);
+    float pa[4], pb[4];
+    {
+        const float x0 = rA01.x - nA01.x, y0 = iA01.x + jA01.x, x1 = rA01.y - nA01.y, y1 = iA01.y + jA01.y;
+        const float x2 = rA23.x - nA23.x, y2 = iA23.x + jA23.x, x3 = rA23.y - nA23.y, y3 = iA23.y + jA23.y;
+        pa[0] = fmaf(x0, x0, y0 * y0) * inv.x; pa[1] = fmaf(x1, x1, y1 * y1) * inv.y;
+        pa[2] = fmaf(x2, x2, y2 * y2) * inv.z; pa[3] = fmaf(x3, x3, y3 * y3) * inv.w;
+    }
+    {
+        const float x0 = rB01.x - nB01.x, y0 = iB01.x + jB01.x, x1 = rB01.y - nB01.y, y1 = iB01.y + jB01.y;
+        const float x2 = rB23.x - nB23.x, y2 = iB23.x + jB23.x, x3 = rB23.y - nB23.y, y3 = iB23.y + jB23.y;
+        pb[0] = fmaf(x0, x0, y0 * y0) * inv.x; pb[1] = fmaf(x1, x1, y1 * y1) * inv.y;
+        pb[2] = fmaf(x2, x2, y2 * y2) * inv.z; pb[3] = fmaf(x3, x3, y3 * y3) * inv.w;
+    }
+    const bool liveA = t < T, liveB = t + 1 < T;
+    const int ndst = bl->ndst;
+    if (liveA) {
+        float va[4], vb[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            va[r] = decibels ? db10(fmaxf(1e-10f, pa[r])) : sqrtf(pa[r]);
+            vb[r] = decibels ? db10(fmaxf(1e-10f, pb[r])) : sqrtf(pb[r]);
+        }
+        float *ot = out + t;
+        const bool pair = vec2 && liveB;
+        // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
+        for (int d = 0; d < ndst; ++d) {
+            const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
+            const int o4[4] = {off.x, off.y, off.z, off.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (o4[r] >= 0) {
+                    float *q = ot + (long long)o4[r] * T;
+                    if (pair) {
+                        *reinterpret_cast<float2 *>(q) = make_float2(va[r], vb[r]);
+                    } else {
+                        q[0] = va[r];
+                        if (liveB) q[1] = vb[r];
+                    }
+                }
+            }
+        }
+    }
+    if (decibels) {
+        float vmax = liveA ? fmaxf(fmaxf(pa[0], pa[1]), fmaxf(pa[2], pa[3])) : 0.f;
+        if (liveB) vmax = fmaxf(vmax, fmaxf(fmaxf(pb[0], pb[1]), fmaxf(pb[2], pb[3])));
+        int have = s_max[bl->chan[0]];
+        for (int d = 1; d < ndst; ++d) have = min(have, s_max[bl->chan[d]]);
+        if (__any_sync(gmask, __float_as_int(vmax) > have)) {
+            for (int o = glanes / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
+            if (leader)
+                for (int d = 0; d < ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+        }
+    }
+}
+#else
+constexpr int kDbufPad = 1;    // odd Dbuf pitch: the transposed writes are conflict free
+#endif
+
 struct CqtParams {
     const float *audio, *ladder;
     float *out;
@@ -726,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
     constexpr int NSUB = kThreads / FL;         // lane groups per CTA
     constexpr int NCHUNK = TT / FL;             // frame chunks per tile
-    constexpr int DP = TT + 1;                  // Dbuf pitch in float2 (odd: transposed writes are conflict free)
+    constexpr int DP = TT + kDbufPad;           // Dbuf pitch in float2
     extern __shared__ __align__(16) float smem[];
     float2 *s_tw1 = reinterpret_cast<float2 *>(smem);                 // NC
     float2 *s_tw2 = s_tw1 + NC;                                       // NC + 2 (k = 0 .. NC, padded)
@@ -854,6 +938,20 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
 
         // Projection.  The lanes of a group hold consecutive frames, so the stores of one row are already T-contiguous
         // (FL * 4 bytes per row and group): results go straight to global memory.
+#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
+        {
+            constexpr int LPB = FL / 2;              // lanes per block: every lane owns two consecutive frames
+            const int sub2 = tid / LPB, lt2 = tid % LPB;
+            const unsigned gm2 = LPB == 32 ? 0xffffffffu : (((1u << LPB) - 1u) << ((lane / LPB) * LPB));
+            const bool vec2 = ((T & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+            for (int w = sub2; w < it.nblk * NCHUNK; w += kThreads / LPB) {
+                const int bi = w / NCHUNK, ch = w % NCHUNK;
+                const CqtBlock4 *bl = s_blk + bi;
+                project_block2(bl, s_w + (bl->woff - it.woff0), Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + 2 * lt2, DP, out, T,
+                               t0 + ch * FL + 2 * lt2, p.decibels, s_max, gm2, LPB, lt2 == 0, vec2);
+            }
+        }
+#else
         for (int w = sub; w < it.nblk * NCHUNK; w += NSUB) {
             const int bi = w / NCHUNK, ch = w % NCHUNK;
             const CqtBlock4 *bl = s_blk + bi;
@@ -929,6 +1027,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 }
             }
         }
+#endif
         // no barrier here: the next iteration's top-of-loop barrier orders these reads before the next FFT's scratch writes
     }
     __syncthreads();
@@ -961,7 +1060,7 @@ constexpr int kSlideMaxItems = 24;          // items per launch (grid.z)
 #define AMT_SLIDE_CTAS 2
 #endif
 constexpr int kSlideFL = AMT_SLIDE_FL;      // frames per projection chunk
-constexpr int kSlideDP = kSlideFL + 1;      // Dbuf pitch (float2)
+constexpr int kSlideDP = kSlideFL + kDbufPad;   // Dbuf pitch (float2)
 
 struct SlideParams {
     const float *audio, *ladder;
@@ -1078,6 +1177,19 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
             }
         }
         __syncthreads();
+#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
+        {
+            constexpr int LPB = FL / 2;
+            const int sub2 = tid / LPB, lt2 = tid % LPB;
+            const unsigned gm2 = LPB == 32 ? 0xffffffffu : (((1u << LPB) - 1u) << (((tid & 31) / LPB) * LPB));
+            const bool vec2 = ((T & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+            for (int w = sub2; w < it.nblk; w += NT / LPB) {
+                const CqtBlock4 *bl = s_blk + w;
+                project_block2(bl, s_w + (bl->woff - it.woff0), Dbuf + (bl->col0 - it.kmin) * DP + 2 * lt2, DP, out, T, t0 + c0 + 2 * lt2,
+                               p.decibels, s_max, gm2, LPB, lt2 == 0, vec2);
+            }
+        }
+#else
         // projection of the chunk: same blocked form as cqt_kernel (lanes along frames, 4 rows per block, packed row pairs)
         for (int w = sub; w < it.nblk; w += NSUB) {
             const CqtBlock4 *bl = s_blk + w;
@@ -1151,6 +1263,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
                 }
             }
         }
+#endif
         __syncthreads();
     }
 }
@@ -1564,7 +1677,7 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
         const int fixed_floats = 2 * NC + 2 * (NC + 2);
         int maxw = 0;
         for (int i = item0; i < item0 + nitems; ++i) maxw = std::max(maxw, p.items[i].wcount);
-        const int dbuf_floats = (maxkb * (TT + 1) * 2 + 3) / 4 * 4;
+        const int dbuf_floats = (maxkb * (TT + kDbufPad) * 2 + 3) / 4 * 4;
         const int blk_floats = maxblk * (int)(sizeof(CqtBlock4) / 4);
         cp.stage_blocks = 0;
         cp.stage_rows = 0;
