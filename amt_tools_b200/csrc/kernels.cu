@@ -36,6 +36,9 @@
 #ifndef AMT_MID_LEVEL
 #define AMT_MID_LEVEL 3        // projection launches are cut by ladder depth: level 0 | 1 .. AMT_MID_LEVEL | deeper
 #endif
+#ifndef AMT_SLIDE_RESEED
+#define AMT_SLIDE_RESEED 8     // frames between exact re-seeds of the sliding-DFT phase P (recurrence P *= W^(k hop) in between)
+#endif
 #ifndef AMT_SLIDE_TILE
 #define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
 #endif
@@ -1047,7 +1050,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
 // One thread owns one bin k of the item's band and walks the frames of a tile: 2 hop real-by-complex MACs with
 // register-resident twiddles + a handful of complex operations per frame instead of an N-point FFT shared by the band
 // (n_fft 1024, hop 8, 207 band bins: ~36 instructions per bin and frame).  Numerics: B is only ever ADDED to (no
-// multiplicative state), with Kahan compensation; P is re-seeded from the exact table every 32 frames; a tile starts
+// multiplicative state), with Kahan compensation; P is re-seeded from the exact table every 8 frames; a tile starts
 // from B = 0 and a lead-in of N / hop sample groups (the first window), so errors never outlive a tile.  Every 32 frames
 // the band spectra are handed to the same blocked projection as cqt_kernel through Dbuf[k][frame].
 // ------------------------------------------------------------------------------------------------
@@ -1147,7 +1150,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     if (active) {
 #pragma unroll 2
         for (int u = 0; u < Q; ++u) {
-            if ((u & 31) == 0) P = seed(t0 - Q + u);
+            if ((u & (AMT_SLIDE_RESEED - 1)) == 0) P = seed(t0 - Q + u);
             step(s_x + u * H);
         }
     }
@@ -1168,10 +1171,10 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << (((tid & 31) / FL) * FL));   // lanes of this frame group
     for (int c0 = 0; c0 < Tt && t0 + c0 < T; c0 += FL) {
         if (active) {
-            P = seed(t0 + c0);
             float2 *dp = Dbuf + tid * DP;
 #pragma unroll 4
             for (int f = 0; f < FL; ++f) {
+                if ((f & (AMT_SLIDE_RESEED - 1)) == 0) P = seed(t0 + c0 + f);
                 dp[f] = make_float2(fmaf(P.x, B.x, P.y * B.y), fmaf(P.x, B.y, -P.y * B.x));   // conj(P) * B
                 step(s_x + (c0 + f) * H);
             }
