@@ -45,3 +45,31 @@ def aggregate_throughput(audio_seconds, elapsed_seconds):
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
         dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
     return total, slowest
+
+
+def bind_host_to_gpu(device_index):
+    """
+    Pins the calling process to the CPU cores next to GPU `device_index` (NVML's ideal affinity), so the pinned staging
+    buffers a rank allocates afterwards land on the NUMA node its PCIe root port hangs off: with one rank per GPU the
+    device-to-host copies of the features (5x the audio) would otherwise all target the node the launcher started on.
+    Returns the affinity list, or None when NVML / the cpuset does not allow it (the data path is unaffected either way).
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+            cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+            allowed = os.sched_getaffinity(0)
+            cpus = sorted(c for c in cpus if c in allowed)
+            if not cpus:
+                return None
+            os.sched_setaffinity(0, cpus)
+            return cpus
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return None

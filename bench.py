@@ -270,6 +270,9 @@ def run_ours(args):
         raise SystemExit('bench.py: no CUDA device; amt_tools_b200 has no CPU compute path')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    # one rank per GPU: run next to it, so the pinned staging buffers are NUMA-local to its PCIe root port
+    from amt_tools_b200 import shard as _shard
+    numa_cpus = None if args.no_bind else _shard.bind_host_to_gpu(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -586,6 +589,7 @@ def run_ours(args):
                    'l2': 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) exceeds the 126 MB L2'
                          % (sum(4 * B * n for n in n_per) / 1e6, (step_bytes - sum(4 * B * n for n in n_per)) / 1e6),
                    'parallelism': 'track-sharded x%d, no collective on the data path' % world,
+                   'host_binding': ('rank pinned to the %d CPU cores next to its GPU (NVML affinity)' % len(numa_cpus)) if numa_cpus else 'none',
                    'streams': ('one CUDA stream per module, consecutive steps alternate between two stream sets (joined at the end of the timed region)'
                                if step_sets else 'one CUDA stream per module, joined every step' if mod_streams else 'single stream')},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
@@ -623,6 +627,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--serial-modules', action='store_true', help='run the modules of a step on one stream (A/B)')
     ap.add_argument('--serial-steps', action='store_true', help='join every step on the current stream (A/B for the step pipelining)')
+    ap.add_argument('--no-bind', action='store_true', help='do not pin the rank to the CPU cores next to its GPU (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -71,3 +71,15 @@ def test_two_rank_gloo_aggregation():
         assert p.exitcode == 0
     assert sorted(i for c in counts for i in c) == list(range(len(lengths)))
     assert abs(total - sum(lengths) / 22050.0) < 1e-9 and slowest == 0.75
+
+
+def test_host_binding_is_optional():
+    # no NVML / no GPU here: the helper must decline quietly and leave the affinity alone
+    import os
+    from amt_tools_b200 import shard
+    before = os.sched_getaffinity(0)
+    cpus = shard.bind_host_to_gpu(0)
+    assert cpus is None or set(cpus) <= before
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
