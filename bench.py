@@ -35,7 +35,7 @@ WORKLOADS = {
     # name: (description, [(module ctor name, kwargs, sample_rate)], clip seconds, default batch per GPU)
     'c5': ('HCQT(22050,hop256,360bins,60bpo,h=.5,1,2,3,4,5)+MelSpec(16000,2048,512,229) on 240 s tracks (configs[4] per-GPU shape)',
            [('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), 22050),
-            ('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000)], 240.0, 4),
+            ('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000)], 240.0, 8),
     'c2': ('MelSpec(16000,2048,512,229) on 64 x 20 s clips (configs[1])',
            [('MelSpec', dict(sample_rate=16000, hop_length=512, n_mels=229, n_fft=2048), 16000)], 20.0, 64),
     'c3': ('HCQT(22050,hop256,360bins,60bpo,6 harmonics) on 30 s clips (configs[2])',
@@ -537,10 +537,14 @@ def run_ours(args):
         ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512, 1>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256, 1>(CqtParams)',
                     'cqt_slide_kernel': 'cqt_slide_kernel(SlideParams)',
                     'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
-        if B == default_batch:
-            traffic = tj.get(args.workload, {}).get(ncu_name)
-            if traffic is not None:   # the capture holds the per-step total of this kernel (it was one launch per step then)
-                traffic = traffic / max(1.0, top[1]['launches_per_step'])
+        cap_b = tj.get('captured_tracks_per_step', {}).get(args.workload)
+        traffic = tj.get(args.workload, {}).get(ncu_name)
+        if traffic is not None and cap_b:
+            # the capture holds the per-step DRAM total of this kernel for `cap_b` tracks per step; every byte belongs to one
+            # track (audio in, features out), so the total scales with the tracks of a step
+            traffic = traffic * (B / float(cap_b)) / max(1.0, top[1]['launches_per_step'])
+        else:
+            traffic = None
     except Exception:
         pass
     roofline = {'kernel': top[0], 'bound': 'hbm', 'achieved': top[1]['algorithmic_GBps'], 'peak': hbm_peak, 'unit': 'GB/s',
