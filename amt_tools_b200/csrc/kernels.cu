@@ -1855,6 +1855,13 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             if (!p.slide_off && is_slide_item(p.items[i])) slide_idx.push_back((int)i);
             else max_fft_level = std::max(max_fft_level, (int)p.items[i].level);
         }
+#ifndef AMT_SLIDE_SORT
+#define AMT_SLIDE_SORT 1
+#endif
+        // CTAs are handed out in grid order (z slowest): the items with the longest tiles (smallest hop: most frames and the longest
+        // lead-in per tile) go first so that they do not form the tail of the launch
+        if (AMT_SLIDE_SORT)
+            std::stable_sort(slide_idx.begin(), slide_idx.end(), [&](int a, int b) { return p.items[a].hop < p.items[b].hop; });
         const int deep_level = std::min(p.n_levels - 1, std::max(max_fft_level, kMidLevel));
         cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_all = nullptr, ev_side = nullptr;
         if (overlap) {
