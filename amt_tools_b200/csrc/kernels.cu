@@ -39,6 +39,9 @@
 #ifndef AMT_SLIDE_RESEED
 #define AMT_SLIDE_RESEED 8     // frames between exact re-seeds of the sliding-DFT phase P (recurrence P *= W^(k hop) in between)
 #endif
+#ifndef AMT_SLIDE_SPLIT
+#define AMT_SLIDE_SPLIT 1      // 0: one launch for all sliding items; 1: bands of at most 128 bins | wider; 2: one launch per CTA size
+#endif
 #ifndef AMT_SLIDE_TILE
 #define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
 #endif
@@ -1623,7 +1626,16 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
             const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= AMT_MID_LEVEL ? 1 : 2;
             if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
         }
-        k += (nslide + kSlideMaxItems - 1) / kSlideMaxItems;
+        (void)nslide;
+        {
+            std::map<int, int> classes;
+            for (const CqtItem &it : p.items)
+                if (!p.slide_off && is_slide_item(it)) {
+                    const int kb = it.kmax - it.kmin + 1;
+                    ++classes[AMT_SLIDE_SPLIT == 0 ? 0 : AMT_SLIDE_SPLIT == 1 ? (kb <= 128 ? 0 : 1) : (kb + 31) / 32];
+                }
+            for (auto &kv : classes) k += (kv.second + kSlideMaxItems - 1) / kSlideMaxItems;
+        }
     } else {
         k += 1;
     }
@@ -1903,7 +1915,17 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
         // The sliding-DFT items follow the ladder on its (high-priority) stream: their few, long-running CTAs start as soon
         // as the deep levels exist and run underneath the FFT-per-frame launches of the shallower levels.
-        if (!slide_idx.empty()) rc = launch_slide(p, cp, slide_idx, batch, maxT, lst);
+        if (!slide_idx.empty()) {
+            // One launch per CTA-size class (narrow bands first: they hold the longest tiles), so that a narrow band does not carry
+            // the idle warps, registers and shared memory of the widest one while it shares the SMs with the FFT launches.
+            std::map<int, std::vector<int>> classes;
+            for (int i : slide_idx) {
+                const int kb = p.items[i].kmax - p.items[i].kmin + 1;
+                classes[AMT_SLIDE_SPLIT == 0 ? 0 : AMT_SLIDE_SPLIT == 1 ? (kb <= 128 ? 0 : 1) : (kb + 31) / 32].push_back(i);
+            }
+            for (auto &kv : classes)
+                if (!rc) rc = launch_slide(p, cp, kv.second, batch, maxT, lst);
+        }
         if (overlap) AMT_CUDA(cudaEventRecord(ev_side, lst));
         auto level_class = [&](int level) { return !overlap ? 0 : level == 0 ? 0 : level <= kMidLevel ? 1 : 2; };
         auto item_class = [&](const CqtItem &it) { return (!p.slide_off && is_slide_item(it)) ? 3 : level_class(it.level); };
