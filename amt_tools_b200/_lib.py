@@ -55,6 +55,7 @@ def _load():
         'amtfeat_feature_size': (C.c_int, [P]),
         'amtfeat_out_shape': (C.c_int, [P, C.c_int64, C.c_int64 * 3, C.POINTER(C.c_int)]),
         'amtfeat_plan_describe': (C.c_int, [P, C.c_char_p, C.c_size_t]),
+        'amtfeat_clip_describe': (C.c_int, [P, C.c_int64, C.c_char_p, C.c_size_t]),
         'amtfeat_workspace_bytes': (C.c_size_t, [P, C.c_int, i64p]),
         'amtfeat_launch_count': (C.c_int, [P, C.c_int, i64p]),
         'amtfeat_process': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, P, C.c_size_t, P]),

@@ -32,19 +32,34 @@ def build(force=False, verbose=False, out=None, defines=()):
     """`out` / `defines` build an A/B variant (tools/variants.py) next to the product library."""
     if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), '-O3', '-std=c++17', '-lineinfo', '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden',
-           '-gencode', 'arch=compute_100a,code=sm_100a', '-x', 'cu',
-           '-Xcompiler', '-DAMTFEAT_BUILD', '-o', out or LIB] + ['-D' + d for d in defines]
+    from concurrent.futures import ThreadPoolExecutor
+    target = out or LIB
+    objdir = os.path.join(HERE, 'build', os.path.basename(target) + '.obj')
+    os.makedirs(objdir, exist_ok=True)
+    common = [_nvcc(), '-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden',
+              '-gencode', 'arch=compute_100a,code=sm_100a', '-x', 'cu', '-Xcompiler', '-DAMTFEAT_BUILD'] + ['-D' + d for d in defines]
     if verbose:
-        cmd += ['-Xptxas', '-v']
-    cmd += [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        common += ['-Xptxas', '-v']
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src + '.o')
+        res = subprocess.run(common + ['-c', os.path.join(CSRC, src), '-o', obj], capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    for src, obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError('nvcc failed compiling %s' % src)
+        if verbose:
+            sys.stderr.write(res.stderr)
+    res = subprocess.run([_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', target] + [o for _, o, _ in results],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError('nvcc failed building libamtfeat.so')
-    if verbose:
-        sys.stderr.write(res.stderr)
-    return out or LIB
+        raise RuntimeError('nvcc failed linking libamtfeat.so')
+    return target
 
 
 if __name__ == '__main__':

@@ -130,6 +130,14 @@ int amtfeat_plan_describe(const amtfeat_plan *plan, char *buf, size_t capacity) 
     return AMTFEAT_OK;
 }
 
+int amtfeat_clip_describe(const amtfeat_plan *plan, int64_t n, char *buf, size_t capacity) {
+    if (!plan || !buf) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    const std::string s = amtfeat::describe_clip(plan->p, n);
+    if (s.size() + 1 > capacity) { amtfeat::set_error("describe buffer too small"); return AMTFEAT_ERR_INVALID; }
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return AMTFEAT_OK;
+}
+
 size_t amtfeat_workspace_bytes(const amtfeat_plan *plan, int batch, const int64_t *n) {
     return amtfeat::workspace_bytes(plan->p, batch, n);
 }

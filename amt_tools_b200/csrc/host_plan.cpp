@@ -14,7 +14,9 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <climits>
 #include <sstream>
+#include <tuple>
 
 #include "plan.h"
 
@@ -89,6 +91,93 @@ static int64_t vqt_lib_frames(const Plan &p, int h, int64_t n) {
         best = std::min<int64_t>(best, 1 + len[l] / hopl);  // centred STFT of the level signal
     }
     return best;
+}
+
+int64_t harmonic_frames(const Plan &p, int h, int64_t n) { return vqt_lib_frames(p, h, n); }
+
+// Geometry of the exact ladders for one clip of n samples (T_all = frames the kernels compute).
+//
+// A harmonic with eds >= 2 is early-downsampled by librosa in ONE resample(2^eds -> 1) call, then decimated 2:1 from
+// octave to octave; the shared ladder reaches the same levels by cascaded 2:1 steps.  In the pass band the two agree to
+// filter ripple (< 2e-7 of the peak), but every cascaded step keeps only samples 0 .. ceil(len / 2) - 1 of its (zero
+// phase) output, as librosa's own octave steps do: the filter's ringing before the first and after the last sample
+// is dropped, whereas the one-shot filter carries it through.  With a 2:1 output m reading inputs 2m - D .. 2m + D,
+// shared level l equals the exact one on [hsafe[l], dev[l]):
+//     hsafe[1] = 0,      hsafe[l] = ceil((hsafe[l-1] + D) / 2)        (tends to D)
+//     dev[1] = len[1],   dev[l]   = ceil((dev[l-1] - D) / 2)          (tends to len - D)
+// Frames whose window leaves that interval -- the first th and the frames from t0 on -- are recomputed from an exact
+// ladder of which only the head [0, hlen) and the tail [first, len) of every level are ever built: level eds in one
+// 2^eds : 1 pass over the audio, deeper levels 2:1 from it.  When the two pieces of a level meet, the whole level is built
+// (first = 0, hlen = -1: the head is read from the tail piece).
+void clip_tail_layout(const Plan &p, int64_t n, int64_t T_all, TailLayout &tl) {
+    for (int l = 0; l < kMaxLevels; ++l) {
+        tl.t0[l] = INT32_MAX;
+        tl.th[l] = 0;
+        tl.dev[l] = INT32_MAX;
+        tl.hsafe[l] = 0;
+        for (int a = 0; a < kMaxAlt; ++a) { tl.first[a][l] = -1; tl.count[a][l] = 0; tl.hlen[a][l] = 0; }
+    }
+    if (p.alts.empty() || n <= 0) return;
+    int32_t len[kMaxLevels];
+    level_lengths(p, n, len);
+    const int64_t D = ((int64_t)p.taps.size() - 1) / 2;
+    int64_t dev = len[1], hs = 0;
+    tl.dev[0] = len[0];
+    tl.dev[1] = len[1];
+    for (int l = 2; l < p.n_levels; ++l) {
+        dev = dev - D <= 0 ? 0 : (dev - D + 1) / 2;
+        hs = (hs + D + 1) / 2;
+        tl.dev[l] = (int32_t)dev;
+        tl.hsafe[l] = (int32_t)std::min<int64_t>(hs, len[l]);
+    }
+    for (int l = 0; l < p.n_levels; ++l) {
+        if (p.alt_nfft_max[l] <= 0) continue;
+        const int64_t hop = p.cfg.hop_length >> l, half = p.alt_nfft_max[l] / 2;
+        // the frames of a tile / chunk of the kernel that holds the shared copy of these rows are skipped or kept together
+        const int64_t A = std::max<int64_t>(32, 16384 / p.alt_nfft_min[l]);
+        const int64_t room = (int64_t)tl.dev[l] - half;                           // frame t stays below dev iff t * hop <= room
+        const int64_t first_alt = room < 0 ? 0 : room / hop + 1;
+        int64_t t0 = first_alt / A * A;
+        int64_t th = (tl.hsafe[l] + half + hop - 1) / hop;                         // frame t starts at or after hsafe iff t * hop >= hsafe + half
+        th = (th + A - 1) / A * A;
+        if (th >= t0) { th = 0; t0 = 0; }                                          // the two regions meet: every frame is exact
+        tl.t0[l] = t0 >= T_all ? INT32_MAX : (int32_t)t0;
+        tl.th[l] = (int32_t)std::min<int64_t>(th, (T_all + A - 1) / A * A);
+    }
+    for (size_t a = 0; a < p.alts.size(); ++a) {
+        const int e = p.alts[a].eds;
+        // head pieces, deepest level first: what the level's own head frames read, and what the next level's head needs
+        int64_t hneed[kMaxLevels] = {};
+        int64_t h_next = 0;
+        for (int l = e + p.n_oct - 1; l >= e; --l) {
+            const int64_t hop = p.cfg.hop_length >> l;
+            int64_t h = tl.th[l] > 0 ? (int64_t)(tl.th[l] - 1) * hop + p.alt_nfft_max[l] / 2 : 0;
+            if (h_next > 0) h = std::max(h, 2 * h_next + D - 1);
+            h = std::min<int64_t>((h + 3) / 4 * 4, len[l]);
+            hneed[l] = h;
+            h_next = h;
+        }
+        int64_t need_next = -1;
+        for (int l = e + p.n_oct - 1; l >= e; --l) {
+            int64_t need = INT64_MAX;
+            if (tl.t0[l] != INT32_MAX) {
+                const int64_t hop = p.cfg.hop_length >> l;
+                need = std::max<int64_t>(0, (int64_t)tl.t0[l] * hop - p.alt_nfft_max[l] / 2);
+            }
+            if (need_next >= 0) need = std::min(need, std::max<int64_t>(0, 2 * need_next - D));
+            if (need != INT64_MAX) need = need / 4 * 4;
+            if (need != INT64_MAX && hneed[l] >= need) {       // head and tail pieces meet: one piece, the whole level
+                need = 0;
+                tl.hlen[a][l] = hneed[l] > 0 ? -1 : 0;
+            } else {
+                tl.hlen[a][l] = (int32_t)hneed[l];
+            }
+            if (need == INT64_MAX) continue;
+            tl.first[a][l] = (int32_t)need;
+            tl.count[a][l] = (int32_t)std::max<int64_t>(0, (int64_t)len[l] - need);
+            need_next = need;
+        }
+    }
 }
 
 static int64_t padded_uncentered(const Plan &p, int64_t n) {
@@ -296,7 +385,7 @@ static double bessel_i0(double x) {
 
 // soxr 'HQ' 2:1 decimator (libsoxr 0.1.3: soxr_quality_spec + lsx_design_lpf): 20-bit precision,
 // passband to (1 - .05 / TO_3dB(rej)) * Nyq_out, stopband from Nyq_out, Kaiser window.
-static std::vector<double> design_decimator() {
+static std::vector<double> design_decimator(int factor = 2) {
     static const double coefs[10][4] = {
         {-6.784957e-10, 1.02856e-05, 0.1087556, -0.8988365 + .001}, {-6.897885e-10, 1.027433e-05, 0.10876, -0.8994658 + .002},
         {-1.000683e-09, 1.030092e-05, 0.1087677, -0.9007898 + .003}, {-3.654474e-10, 1.040631e-05, 0.1087085, -0.8977766 + .006},
@@ -307,7 +396,7 @@ static std::vector<double> design_decimator() {
     const double rej = bits * l2db;
     const double to3db = (1.6e-6 * rej - 7.5e-4) * rej + .646;
     const double att = (bits + 1) * l2db;
-    double Fp = (1.0 - .05 / to3db) / 2.0, Fs = 1.0 / 2.0;  // relative to the input Nyquist
+    double Fp = (1.0 - .05 / to3db) / (double)factor, Fs = 1.0 / (double)factor;  // relative to the input Nyquist
     double tr_bw = std::min(.5 * (Fs - Fp), .5 * Fs);
     const double Fc = Fs - tr_bw;
     const double realm = std::log(tr_bw * .5 / Fc / .0005) / std::log(2.0);
@@ -392,17 +481,23 @@ static int build_vqt(Plan &p) {
         tapsd.push_back(0.0);
     }
     p.taps.resize(tapsd.size());
-    for (size_t i = 0; i < tapsd.size(); ++i) p.taps[i] = (float)(tapsd[i] * std::sqrt(2.0));
+    p.taps64.resize(tapsd.size());
+    for (size_t i = 0; i < tapsd.size(); ++i) {
+        p.taps64[i] = tapsd[i] * std::sqrt(2.0);
+        p.taps[i] = (float)p.taps64[i];
+    }
     // frequency response of the (float32) taps for the fast-convolution decimator: 2048-point blocks, every other
     // output kept => the 2048-point spectrum folds onto 1024 points; a block yields 1024 - D outputs
     p.decim_hh.clear();
     {
         const char *env = std::getenv("AMTFEAT_DECIM");
-        p.decim_direct = env && std::string(env) == "direct";
+        p.decim_mode = !env ? 0 : std::string(env) == "direct" ? 2 : std::string(env) == "fft32" ? 1 : 0;
         const char *env_s = std::getenv("AMTFEAT_SLIDE");
         p.slide_off = env_s && std::string(env_s) == "0";
         const char *env_q = std::getenv("AMTFEAT_SERIAL");
         p.serial_launch = env_q && std::string(env_q) == "1";
+        const char *env_x = std::getenv("AMTFEAT_EXACT_EDS");
+        p.exact_eds = !(env_x && std::string(env_x) == "0");
         const int nt = (int)p.taps.size(), D = (nt - 1) / 2;
         if (1024 - D >= 256) {
             build_fft_tables(p, 2048);
@@ -418,12 +513,39 @@ static int build_vqt(Plan &p) {
             p.decim_hh.resize(513);
             for (int k = 0; k <= 512; ++k)
                 p.decim_hh[k] = cfloat4{(float)H[k].real(), (float)H[k].imag(), (float)H[1024 - k].real(), (float)-H[1024 - k].imag()};
+            // float64 form (decimate_fft64_kernel): the full 2048-point response of the (unrounded) taps, Hermitian
+            // extension, same 1 / 2048, and exp(-2 pi i m / 2048), m < 1024, for its transforms
+            std::vector<std::complex<double>> H64(1025);
+            for (int k = 0; k <= 1024; ++k) {
+                std::complex<double> acc(0, 0);
+                for (int j = 0; j < nt; ++j) {
+                    const double ang = -2.0 * kPi * (double)((long long)j * k % 2048) / 2048.0;
+                    acc += tapsd[j] * std::sqrt(2.0) * std::complex<double>(std::cos(ang), std::sin(ang));   // the float64 design, unrounded
+                }
+                H64[k] = acc / 2048.0;
+            }
+            p.decim_h64.resize(2 * 2048);
+            for (int k = 0; k < 2048; ++k) {
+                const std::complex<double> v = k <= 1024 ? H64[k] : std::conj(H64[2048 - k]);
+                p.decim_h64[2 * k] = v.real();
+                p.decim_h64[2 * k + 1] = v.imag();
+            }
+            p.decim_tw64.resize(2 * 1024);
+            for (int m = 0; m < 1024; ++m) {
+                // exact octant symmetries keep cos / sin accurate to the last bit where it matters (m = 0, 512)
+                const double ang = -2.0 * kPi * (double)m / 2048.0;
+                p.decim_tw64[2 * m] = m == 512 ? 0.0 : std::cos(ang);
+                p.decim_tw64[2 * m + 1] = m == 0 ? 0.0 : std::sin(ang);
+            }
         }
     }
 
     p.harm.clear();
+    p.alts.clear();
+    p.alt_mask = 0;
+    for (int l = 0; l < kMaxLevels; ++l) p.alt_nfft_max[l] = p.alt_nfft_min[l] = 0;
     p.n_levels = 0;
-    std::map<std::pair<int, int>, std::vector<CqtRow>> groups;  // (nfft, level) -> rows
+    std::map<std::tuple<int, int, int>, std::vector<CqtRow>> groups;  // (0 = shared ladder | a + 1 = exact ladder a, nfft, level) -> rows
     for (int h = 0; h < c.n_harmonics; ++h) {
         HarmonicInfo hi;
         hi.fmin = c.harmonics[h] * c.fmin;  // hvqt.py:47
@@ -447,6 +569,25 @@ static int build_vqt(Plan &p) {
         };
         hi.eds_ref = eds_of(cutoff_ref);
         hi.eds_lib = eds_of(cutoff_lib);
+        hi.alt = -1;
+        if (hi.eds_lib >= 2 && p.exact_eds) {
+            // librosa downsamples this harmonic by 2^eds in ONE resample call (constantq.py __early_downsample): its tail
+            // frames come from an exact ladder (clip_tail_layout); harmonics with the same eds share one
+            for (size_t a = 0; a < p.alts.size(); ++a)
+                if (p.alts[a].eds == hi.eds_lib) hi.alt = (int)a;
+            if (hi.alt < 0) {
+                if ((int)p.alts.size() >= kMaxAlt) { set_error("too many distinct early-downsampling factors among the harmonics"); return AMTFEAT_ERR_INVALID; }
+                AltLadder al;
+                al.eds = hi.eds_lib;
+                const int factor = 1 << hi.eds_lib;
+                std::vector<double> t = design_decimator(factor);
+                al.taps.resize(t.size());
+                for (size_t i = 0; i < t.size(); ++i) al.taps[i] = t[i] * std::sqrt((double)factor);
+                hi.alt = (int)p.alts.size();
+                p.alts.push_back(std::move(al));
+            }
+            p.alt_mask |= 1u << h;
+        }
         p.harm.push_back(hi);
         const int eds = hi.eds_lib;
         const double sr_post = sr0 / std::ldexp(1.0, eds);
@@ -525,7 +666,12 @@ static int build_vqt(Plan &p) {
                     std::complex<double> w = mags[q] >= thr ? a[q] * oct_scale : std::complex<double>(0, 0);
                     p.weights.push_back({(float)w.real(), (float)w.imag()});
                 }
-                groups[{nfft, level}].push_back(row);
+                groups[std::make_tuple(0, nfft, level)].push_back(row);
+                if (hi.alt >= 0) {
+                    groups[std::make_tuple(hi.alt + 1, nfft, level)].push_back(row);
+                    p.alt_nfft_max[level] = std::max(p.alt_nfft_max[level], nfft);
+                    p.alt_nfft_min[level] = p.alt_nfft_min[level] ? std::min(p.alt_nfft_min[level], nfft) : nfft;
+                }
             }
         }
     }
@@ -536,8 +682,9 @@ static int build_vqt(Plan &p) {
     p.weights4.clear();
     for (auto &g : groups) {
         CqtItem it{};
-        it.nfft = g.first.first;
-        it.level = g.first.second;
+        it.alt = std::get<0>(g.first);
+        it.nfft = std::get<1>(g.first);
+        it.level = std::get<2>(g.first);
         it.hop = c.hop_length >> it.level;
         it.nrows = (int32_t)g.second.size();
         it.kmin = INT32_MAX;
@@ -609,14 +756,9 @@ static int build_vqt(Plan &p) {
                         w[2 * r + 1] = v.y;
                     }
                 }
-#if AMT_PROJ_PACKED
                 // row pairs side by side: (re0, re1, im0, im1), (re2, re3, im2, im3) -- operands of the packed FFMA2 projection
                 p.weights4[(size_t)bl.woff + 2 * st] = cfloat4{w[0], w[2], w[1], w[3]};
                 p.weights4[(size_t)bl.woff + 2 * st + 1] = cfloat4{w[4], w[6], w[5], w[7]};
-#else
-                p.weights4[(size_t)bl.woff + 2 * st] = cfloat4{w[0], w[1], w[2], w[3]};
-                p.weights4[(size_t)bl.woff + 2 * st + 1] = cfloat4{w[4], w[5], w[6], w[7]};
-#endif
             }
             it.kmin = std::min(it.kmin, lo);
             it.kmax = std::max(it.kmax, hi - 1);
@@ -682,14 +824,21 @@ int build_plan_tables(Plan &p) {
     }
 }
 
+const char *decimator_name(const Plan &p) {
+    if (p.decim_mode == 2 || (p.decim_mode == 1 && p.decim_hh.empty()) || (p.decim_mode == 0 && p.decim_h64.empty())) return "direct";
+    return p.decim_mode == 1 ? "fft32" : "fft64";
+}
+
 std::string describe(const Plan &p) {
     const amtfeat_config &c = p.cfg;
     std::ostringstream o;
     o << "{\"kind\": " << c.kind << ", \"channels\": " << p.C << ", \"feature_size\": " << p.F << ", \"device\": " << p.device;
     if (c.kind == AMTFEAT_MEL) o << ", \"mel_nnz\": " << p.mel_w.size();
     if (c.kind == AMTFEAT_VQT || c.kind == AMTFEAT_HVQT) {
-        o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size() << ", \"decimator\": \"" << ((p.decim_hh.empty() || p.decim_direct) ? "direct" : "fft") << "\""
-          << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_nnz\": " << p.weights4.size() * 2 << ", \"eds_ref\": [";
+        o << ", \"n_octaves\": " << p.n_oct << ", \"n_levels\": " << p.n_levels << ", \"decim_taps\": " << p.taps.size() << ", \"decimator\": \"" << decimator_name(p) << "\""
+          << ", \"basis_nnz\": " << p.weights.size() << ", \"padded_block_nnz\": " << p.weights4.size() * 2 << ", \"exact_ladders\": [";
+        for (size_t a = 0; a < p.alts.size(); ++a) o << (a ? ", " : "") << "{\"eds\": " << p.alts[a].eds << ", \"taps\": " << p.alts[a].taps.size() << "}";
+        o << "], \"alt_mask\": " << p.alt_mask << ", \"eds_ref\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_ref;
         o << "], \"eds_lib\": [";
         for (size_t h = 0; h < p.harm.size(); ++h) o << (h ? ", " : "") << p.harm[h].eds_lib;
@@ -698,7 +847,51 @@ std::string describe(const Plan &p) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
               << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"unique_rows\": " << it.nuniq << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax
-              << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << "}";
+              << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << ", \"alt\": " << it.alt << "}";
+        }
+        o << "]";
+    }
+    o << "}";
+    return o.str();
+}
+
+std::string describe_clip(const Plan &p, int64_t n) {
+    std::ostringstream o;
+    const int64_t T = output_frames(p, n);
+    o << "{\"frames\": " << T;
+    if (p.cfg.kind == AMTFEAT_VQT || p.cfg.kind == AMTFEAT_HVQT) {
+        int64_t T_all = T;
+        o << ", \"harmonic_frames\": [";
+        for (size_t h = 0; h < p.harm.size(); ++h) {
+            const int64_t th = harmonic_frames(p, (int)h, n);
+            if (p.cfg.kind == AMTFEAT_HVQT && p.cfg.decibels) T_all = std::max(T_all, th);
+            o << (h ? ", " : "") << th;
+        }
+        int32_t len[kMaxLevels];
+        level_lengths(p, n, len);
+        o << "], \"frames_computed\": " << T_all << ", \"decim_delay\": " << ((int64_t)p.taps.size() - 1) / 2 << ", \"level_len\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << len[l];
+        TailLayout tl;
+        clip_tail_layout(p, n, T_all, tl);
+        o << "], \"dev\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << (tl.dev[l] == INT32_MAX ? -1 : tl.dev[l]);
+        o << "], \"hsafe\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << tl.hsafe[l];
+        o << "], \"alt_th\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << tl.th[l];
+        o << "], \"alt_t0\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << (tl.t0[l] == INT32_MAX ? -1 : tl.t0[l]);
+        o << "], \"alt_nfft_max\": [";
+        for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << p.alt_nfft_max[l];
+        o << "], \"exact_ladders\": [";
+        for (size_t a = 0; a < p.alts.size(); ++a) {
+            o << (a ? ", " : "") << "{\"eds\": " << p.alts[a].eds << ", \"first\": [";
+            for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << tl.first[a][l];
+            o << "], \"count\": [";
+            for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << tl.count[a][l];
+            o << "], \"head\": [";
+            for (int l = 0; l < p.n_levels; ++l) o << (l ? ", " : "") << tl.hlen[a][l];
+            o << "]}";
         }
         o << "]";
     }

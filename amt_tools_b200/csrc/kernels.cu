@@ -37,16 +37,13 @@
 #define AMT_MID_LEVEL 3        // projection launches are cut by ladder depth: level 0 | 1 .. AMT_MID_LEVEL | deeper
 #endif
 #ifndef AMT_SLIDE_RESEED
-#define AMT_SLIDE_RESEED 8     // frames between exact re-seeds of the sliding-DFT phase P (recurrence P *= W^(k hop) in between)
-#endif
+#define AMT_SLIDE_RESEED 8     // most frames between exact re-seeds of the sliding-DFT phase P (recurrence P *= W^(k hop) in between);
+#endif                         // the interval shrinks with the hop: 16 / hop frames (hop 16: every frame, hop 8: every other one)
 #ifndef AMT_SLIDE_SPLIT
 #define AMT_SLIDE_SPLIT 1      // 0: one launch for all sliding items; 1: bands of at most 128 bins | wider; 2: one launch per CTA size
 #endif
 #ifndef AMT_SLIDE_TILE
 #define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
-#endif
-#ifndef AMT_PROJ_FPL
-#define AMT_PROJ_FPL 2         // frames per lane in the blocked projection (2: one 16-byte load feeds two frames, 8-byte stores)
 #endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
@@ -672,16 +669,197 @@ __global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFf
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4 (default form) : the same overlap-save decimator in FLOAT64.
+//   The float32 forms above are ~1e-7 of the block amplitude off per ladder step, white, and that noise stays in the
+//   band while the strong high-frequency content it came from is filtered away: on the deep levels it was the largest
+//   term of the dB error (measured: 6e-4 .. 1e-3 dB on bins within 60 dB of the maximum; with an exact ladder the rest
+//   of the path is at 2e-4 .. 3e-4).  Here every level is the correctly rounded float32 of an exact decimation.
+//   One CTA takes the two blocks as ONE complex signal z = uA + i uB (h is real, so z (*) h = uA (*) h + i uB (*) h):
+//   2048-point complex DFT, spectral product with H, fold W[k] + W[k + 1024] (keeps every other output sample),
+//   1024-point inverse DFT -> ydA + i ydB.  Stockham autosort passes in shared memory (radix 4, one radix 2), twiddles from
+//   a float64 table; ~100 float64 flop per output sample.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int kD64Threads = 256;
+
+struct Dec64Params {
+    const float *audio;
+    float *ladder;
+    const ClipMeta *meta;
+    const double2 *tw;   // exp(-2 pi i m / 2048), m < 1024
+    const double2 *H;    // response of the taps, k < 2048, times 1 / 2048
+    int level_out, D, M, pairs_per_cta;
+};
+
+__device__ __forceinline__ double2 dmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 dadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 dsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// exp(-2 pi i m / 2048), 0 <= m < 2048, from the half table
+__device__ __forceinline__ double2 tw2048(const double2 *tw, int m) {
+    const double2 w = tw[m & 1023];
+    return (m & 1024) ? make_double2(-w.x, -w.y) : w;
+}
+
+// One Stockham pass of an N-point forward DFT (radix R, sub-transform size Ns so far): thread j takes inputs j + r N / R,
+// twiddles them by exp(-2 pi i r (j mod Ns) / (Ns R)), and writes the R-point DFT to (j / Ns) Ns R + (j mod Ns) + r Ns.
+template <int N, int R>
+__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw,
+                                              int Ns, int tid) {
+    const int stride = 2048 / (Ns * R);
+    for (int j = tid; j < N / R; j += kD64Threads) {
+        const int k = j & (Ns - 1);
+        double2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[j + r * (N / R)];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = dmul(v[r], tw2048(tw, r * k * stride));
+        }
+        const int j0 = (j - k) * R + k;
+        if (R == 4) {
+            const double2 a = dadd(v[0], v[2]), b = dsub(v[0], v[2]), c = dadd(v[1], v[3]), d = dsub(v[1], v[3]);
+            const double2 dmi = make_double2(d.y, -d.x);   // -i d
+            out[j0] = dadd(a, c);
+            out[j0 + Ns] = dadd(b, dmi);
+            out[j0 + 2 * Ns] = dsub(a, c);
+            out[j0 + 3 * Ns] = dsub(b, dmi);
+        } else {
+            out[j0] = dadd(v[0], v[1]);
+            out[j0 + Ns] = dsub(v[0], v[1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kD64Threads, 2) decimate_fft64_kernel(const Dec64Params p) {
+    extern __shared__ __align__(16) double2 smem64[];
+    double2 *s_tw = smem64, *b0 = s_tw + 1024, *b1 = b0 + 2048;
+    const int tid = threadIdx.x;
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    const int len_out = cm->lvl_len[p.level_out], len_in = cm->lvl_len[p.level_out - 1];
+    const int npairs = (int)(((long long)len_out + 2 * p.M - 1) / (2 * p.M));
+    const int pair0 = blockIdx.x * p.pairs_per_cta;
+    if (pair0 >= npairs) return;
+    const int pair1 = min(npairs, pair0 + p.pairs_per_cta);
+    for (int i = tid; i < 1024; i += kD64Threads) s_tw[i] = p.tw[i];
+    const float *src = (p.level_out == 1 ? p.audio : p.ladder) + cm->lvl_off[p.level_out - 1];
+    float *dst = p.ladder + cm->lvl_off[p.level_out];
+    for (int pair = pair0; pair < pair1; ++pair) {
+        const long long mA = (long long)pair * 2 * p.M, mB = mA + p.M;
+        const bool haveB = mB < len_out;
+        const long long baseA = 2 * mA - p.D, baseB = 2 * mB - p.D;
+        __syncthreads();   // the previous pair's result has been read (first time: nothing)
+        for (int n = tid; n < 2048; n += kD64Threads) {
+            const long long ia = baseA + n, ib = baseB + n;
+            const float xa = (ia >= 0 && ia < len_in) ? __ldg(src + ia) : 0.f;
+            const float xb = (haveB && ib >= 0 && ib < len_in) ? __ldg(src + ib) : 0.f;
+            b0[n] = make_double2((double)xa, (double)xb);
+        }
+        __syncthreads();   // (also covers the twiddle table the first time)
+        stockham_pass<2048, 4>(b0, b1, s_tw, 1, tid);    __syncthreads();
+        stockham_pass<2048, 4>(b1, b0, s_tw, 4, tid);    __syncthreads();
+        stockham_pass<2048, 4>(b0, b1, s_tw, 16, tid);   __syncthreads();
+        stockham_pass<2048, 4>(b1, b0, s_tw, 64, tid);   __syncthreads();
+        stockham_pass<2048, 4>(b0, b1, s_tw, 256, tid);  __syncthreads();
+        stockham_pass<2048, 2>(b1, b0, s_tw, 1024, tid); __syncthreads();
+        // spectral product, fold onto 1024 points, conjugate (the inverse transform is conj(DFT(conj .)))
+        for (int k = tid; k < 1024; k += kD64Threads) {
+            const double2 w0 = dmul(b0[k], __ldg(p.H + k)), w1 = dmul(b0[k + 1024], __ldg(p.H + k + 1024));
+            b1[k] = make_double2(w0.x + w1.x, -(w0.y + w1.y));
+        }
+        __syncthreads();
+        stockham_pass<1024, 4>(b1, b0, s_tw, 1, tid);    __syncthreads();
+        stockham_pass<1024, 4>(b0, b1, s_tw, 4, tid);    __syncthreads();
+        stockham_pass<1024, 4>(b1, b0, s_tw, 16, tid);   __syncthreads();
+        stockham_pass<1024, 4>(b0, b1, s_tw, 64, tid);   __syncthreads();
+        stockham_pass<1024, 4>(b1, b0, s_tw, 256, tid);  __syncthreads();
+        // b0[j] = conj(ydA[j] + i ydB[j]); output m = m0 + j - D for j >= D
+        for (int j = p.D + tid; j < 1024; j += kD64Threads) {
+            const double2 r = b0[j];
+            const long long ma = mA + j - p.D, mb = mB + j - p.D;
+            if (ma < len_out) dst[ma] = (float)r.x;
+            if (haveB && mb < len_out) dst[mb] = (float)(-r.y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact ladders (harmonics with eds >= 2): one level of the TAIL of an exact ladder, direct form, float64 accumulation.
+//   level_in == 0: ONE factor : 1 decimation of the audio (librosa __early_downsample: a single resample call);
+//   level_in >= 1: the 2:1 step from the previous exact level.  y[m] = sum_k h[k] x[factor m + D - k], zero extension.
+// Only samples m >= alt_first[level_out] are produced (clip_tail_layout): a few thousand per clip.
+// ------------------------------------------------------------------------------------------------
+
+struct TailParams {
+    const float *audio;
+    float *ladder;
+    const ClipMeta *meta;
+    const double *taps;
+    int ntaps, factor, level_in, level_out, alt, head;   // head: the head piece [0, alt_hlen) instead of the tail piece [alt_first, len)
+};
+
+__global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
+    const ClipMeta *cm = p.meta + blockIdx.y;
+    long long first, end;
+    float *dst;
+    if (p.head) {
+        // a head piece that is part of the tail piece (alt_hoff == alt_off: whole level stored) is produced by the tail pass
+        if (cm->alt_hlen[p.alt][p.level_out] <= 0 || cm->alt_first[p.alt][p.level_out] == 0) return;
+        first = 0;
+        end = cm->alt_hlen[p.alt][p.level_out];
+        dst = p.ladder + cm->alt_hoff[p.alt][p.level_out];
+    } else {
+        first = cm->alt_first[p.alt][p.level_out];
+        if (first < 0) return;
+        end = cm->lvl_len[p.level_out];
+        dst = p.ladder + cm->alt_off[p.alt][p.level_out];
+    }
+    const long long m = first + (long long)blockIdx.x * kThreads + threadIdx.x;
+    if (m >= end) return;
+    const float *src;
+    long long lo, hi;   // samples of the input piece that exist; everything outside reads as zero (true for < 0 and >= len; the
+                        // geometry guarantees that nothing else is ever asked for, tests/test_exact_ladder.py)
+    if (p.level_in == 0) {
+        src = p.audio + cm->in_off;
+        lo = 0;
+        hi = cm->n;
+    } else if (p.head && cm->alt_first[p.alt][p.level_in] != 0) {
+        src = p.ladder + cm->alt_hoff[p.alt][p.level_in];
+        lo = 0;
+        hi = cm->alt_hlen[p.alt][p.level_in];
+    } else {
+        src = p.ladder + cm->alt_off[p.alt][p.level_in];
+        lo = cm->alt_first[p.alt][p.level_in];
+        hi = cm->lvl_len[p.level_in];
+    }
+    const int D = (p.ntaps - 1) / 2;
+    const long long c = (long long)p.factor * m + D;
+    // i = c - k must lie in [lo, hi)
+    const long long k_lo = max(0ll, c - hi + 1), k_hi = min((long long)p.ntaps - 1, c - lo);
+    double acc = 0.0;
+    for (long long k = k_lo; k <= k_hi; ++k) acc = fma(__ldg(p.taps + k), (double)src[c - k], acc);
+    dst[m] = (float)acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 + K5 : CQT / VQT / HCQT response of one (ladder level, n_fft) item
 // ------------------------------------------------------------------------------------------------
 
-#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
 constexpr int kDbufPad = 2;    // even Dbuf pitch: the two frames of a lane are one aligned 16-byte load
 // Projection of one block of 4 rows for the TWO consecutive frames (t, t + 1) this lane owns: every step is one 16-byte load of
 // the band spectra of both frames + the block's two warp-uniform weight vectors feeding 16 packed FFMA2; |.|^2 / L -> dB or
 // magnitude -> 8-byte stores (vec2: the clip's rows are 8-byte aligned and T is even) + lazy per-(clip, channel) maximum.
+// `skip`: channels whose frames of this tile / chunk come from an exact ladder instead (group-uniform); `tmax`: per channel, the
+// frames its dB maximum runs over (frames in [T, tmax) are computed for the maximum only, hvqt.py:123-128).
 __device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4 *wt, const float2 *Dp, int DP, float *out, int T, int t,
-                                               int decibels, int *s_max, unsigned gmask, int glanes, bool leader, bool vec2) {
+                                               int decibels, int *s_max, unsigned gmask, int glanes, bool leader, bool vec2,
+                                               unsigned skip, const int *__restrict__ tmax) {
+    const int ndst = bl->ndst;
+    unsigned live_d = 0;
+    for (int d = 0; d < ndst; ++d)
+        if (!((skip >> bl->chan[d]) & 1u)) live_d |= 1u << d;
+    if (!live_d) return;
     const int steps = bl->steps;
     const float2 z2 = make_float2(0.f, 0.f);
     float2 rA01 = z2, nA01 = z2, iA01 = z2, jA01 = z2, rA23 = z2, nA23 = z2, iA23 = z2, jA23 = z2;
@@ -712,7 +890,6 @@ __device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4
         pb[2] = fmaf(x2, x2, y2 * y2) * inv.z; pb[3] = fmaf(x3, x3, y3 * y3) * inv.w;
     }
     const bool liveA = t < T, liveB = t + 1 < T;
-    const int ndst = bl->ndst;
     if (liveA) {
         float va[4], vb[4];
 #pragma unroll
@@ -724,6 +901,7 @@ __device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4
         const bool pair = vec2 && liveB;
         // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
         for (int d = 0; d < ndst; ++d) {
+            if (!((live_d >> d) & 1u)) continue;
             const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
             const int o4[4] = {off.x, off.y, off.z, off.w};
 #pragma unroll
@@ -743,18 +921,27 @@ __device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4
     if (decibels) {
         float vmax = liveA ? fmaxf(fmaxf(pa[0], pa[1]), fmaxf(pa[2], pa[3])) : 0.f;
         if (liveB) vmax = fmaxf(vmax, fmaxf(fmaxf(pb[0], pb[1]), fmaxf(pb[2], pb[3])));
-        int have = s_max[bl->chan[0]];
-        for (int d = 1; d < ndst; ++d) have = min(have, s_max[bl->chan[d]]);
+        int have = 0x7fffffff;
+        for (int d = 0; d < ndst; ++d)
+            if ((live_d >> d) & 1u) have = min(have, s_max[bl->chan[d]]);
         if (__any_sync(gmask, __float_as_int(vmax) > have)) {
             for (int o = glanes / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
             if (leader)
-                for (int d = 0; d < ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+                for (int d = 0; d < ndst; ++d)
+                    if ((live_d >> d) & 1u) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
+        }
+        if (t + 1 >= T) {
+            // frames past the trimmed output: they only count for the maximum of a harmonic whose own VQT is that long
+            const float ma = fmaxf(fmaxf(pa[0], pa[1]), fmaxf(pa[2], pa[3])), mb = fmaxf(fmaxf(pb[0], pb[1]), fmaxf(pb[2], pb[3]));
+            for (int d = 0; d < ndst; ++d) {
+                if (!((live_d >> d) & 1u)) continue;
+                const int lim = __ldg(tmax + bl->chan[d]);
+                if (t >= T && t < lim) atomicMax(&s_max[bl->chan[d]], __float_as_int(ma));
+                if (t + 1 >= T && t + 1 < lim) atomicMax(&s_max[bl->chan[d]], __float_as_int(mb));
+            }
         }
     }
 }
-#else
-constexpr int kDbufPad = 1;    // odd Dbuf pitch: the transposed writes are conflict free
-#endif
 
 struct CqtParams {
     const float *audio, *ladder;
@@ -768,11 +955,50 @@ struct CqtParams {
     const float2 *weights;
     const float2 *tw1, *tw2;
     int C, F, decibels, tile_floats, stage_blocks, stage_rows, dbuf_off, w_off, blk_off, region_floats, tiles_per_cta;
+    unsigned alt_mask;   // channels whose tail frames come from an exact ladder (Plan::alt_mask)
+};
+
+// Level signal an item frames: the shared ladder, or (exact-ladder item) the head / tail piece of an exact level (the tail
+// through its virtual offset).  `len` is the length to zero-fill beyond: the level's, or the head piece's.
+__device__ __forceinline__ const float *item_signal(const CqtItem &it, const ClipMeta *cm, const float *audio, const float *ladder,
+                                                    bool head, long long &len) {
+    len = cm->lvl_len[it.level];
+    if (it.alt) {
+        if (head) {
+            len = cm->alt_hlen[it.alt - 1][it.level];
+            return ladder + cm->alt_hoff[it.alt - 1][it.level];
+        }
+        return ladder + cm->alt_off[it.alt - 1][it.level];
+    }
+    return (it.level == 0 ? audio : ladder) + cm->lvl_off[it.level];
+}
+
+// Frames an item computes, as tiles of TT frames.  Shared-ladder item: tiles 0 .. over [0, Tall); its copy of exact-ladder rows
+// skips the tiles inside [0, th) and [t0, Tall).  Exact-ladder item: `nhead` tiles over [0, min(th, Tall)), then the tiles from t0.
+struct TileMap {
+    int th, t0, nhead, ntiles, TT;
+    bool alt;
+    __device__ __forceinline__ TileMap(const CqtItem &it, const ClipMeta *cm, int Tall, int TT_) : TT(TT_), alt(it.alt != 0) {
+        th = cm->alt_th[it.level];
+        t0 = cm->alt_t0[it.level];
+        if (alt) {
+            nhead = (min(th, Tall) + TT - 1) / TT;
+            ntiles = nhead + (t0 < Tall ? (Tall - t0 + TT - 1) / TT : 0);
+        } else {
+            nhead = 0;
+            ntiles = (Tall + TT - 1) / TT;
+        }
+    }
+    __device__ __forceinline__ bool head(int tile) const { return alt && tile < nhead; }
+    __device__ __forceinline__ int first_frame(int tile) const { return (!alt || tile < nhead) ? tile * TT : t0 + (tile - nhead) * TT; }
+    // frames of a head tile end at th (th is a multiple of every tile size); everything else runs to Tall
+    __device__ __forceinline__ int frame_end(int tile, int Tall) const { return head(tile) ? min(th, Tall) : Tall; }
+    __device__ __forceinline__ unsigned skip(int t, unsigned alt_mask) const { return (!alt && (t < th || t >= t0)) ? alt_mask : 0u; }
 };
 
 // Shared prologue of both CQT kernels: stage the level signal, run the warp FFT unit.
 template <int NC>
-__device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem &it, const ClipMeta *cm, int t0, float2 *s_tw1,
+__device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem &it, const ClipMeta *cm, int t0, bool head, float2 *s_tw1,
                                               float2 *s_tw2, float *s_scr, float *s_tile) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, TT = kWarpsPerCta * G, NFFT = 2 * NC, WP2 = L::WARP_PITCH / 2;
@@ -781,9 +1007,10 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
     for (int i = tid; i < NC; i += kThreads) s_tw1[i] = p.tw1[i];
     for (int i = tid; i <= NC; i += kThreads) s_tw2[i] = p.tw2[i];
 #endif
-    const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
+    long long len;
+    const float *src = item_signal(it, cm, p.audio, p.ladder, head, len);
     int shift, fstride;
-    load_tile(s_tile, src, cm->lvl_len[it.level], (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
+    load_tile(s_tile, src, len, (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
     __syncthreads();
     float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
     const bool vec_ok = ((shift | fstride) & 1) == 0;
@@ -814,7 +1041,6 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2, NFFT = 2 * NC;
     constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
-    constexpr int NSUB = kThreads / FL;         // lane groups per CTA
     constexpr int NCHUNK = TT / FL;             // frame chunks per tile
     constexpr int DP = TT + kDbufPad;           // Dbuf pitch in float2
     extern __shared__ __align__(16) float smem[];
@@ -826,14 +1052,15 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
-    const int T = cm->T;
-    const int ntiles = (T + TT - 1) / TT;
-    const int tile_begin = blockIdx.x * p.tiles_per_cta;
-    if (tile_begin >= ntiles) return;
-    const int tile_end = min(ntiles, tile_begin + p.tiles_per_cta);
+    const int T = cm->T, Tall = cm->T_all;
     const CqtItem it = p.items[blockIdx.z];
-    const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
-    const long long len = cm->lvl_len[it.level];
+    // an exact-ladder item covers the first and the last frames of its level; the shared copy of those rows skips them
+    const TileMap tm(it, cm, Tall, TT);
+    const int tile_begin = blockIdx.x * p.tiles_per_cta;
+    if (tile_begin >= tm.ntiles) return;
+    const int tile_end = min(tm.ntiles, tile_begin + p.tiles_per_cta);
+    long long len;
+    const float *src = item_signal(it, cm, p.audio, p.ladder, tm.head(tile_begin), len);
     const bool overlap = it.hop <= NFFT;
     if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
 
@@ -850,7 +1077,7 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
         }
     }
     int shift = 0, fstride = overlap ? it.hop : NFFT;
-    if (overlap) load_tile_async(s_tile, src, len, (long long)tile_begin * TT * it.hop - NC, it.hop, NFFT, TT, tid, shift);
+    if (overlap) load_tile_async(s_tile, src, len, (long long)tm.first_frame(tile_begin) * it.hop - NC, it.hop, NFFT, TT, tid, shift);
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 
     // phase-B layout of the region
@@ -858,17 +1085,17 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
     float4 *s_w = reinterpret_cast<float4 *>(s_reg + p.w_off);
     const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_reg + p.blk_off);   // the item's block descriptors
     float *out = p.out + cm->out_off;
-    const int sub = tid / FL, lt = tid % FL;
-    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << ((lane / FL) * FL));  // lanes of this frame group
     const int kb = it.kmax - it.kmin + 1;
 
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int t0 = tile * TT;
+        const int t0 = tm.first_frame(tile);
+        const unsigned skip = tm.skip(t0, p.alt_mask);
         if (overlap) {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();   // previous iteration's readers of the region are done
+            src = item_signal(it, cm, p.audio, p.ladder, tm.head(tile), len);
             load_tile(s_tile, src, len, (long long)t0 * it.hop - NC, it.hop, NFFT, TT, tid, shift, fstride);
         }
         __syncthreads();       // tile (and, first time, the twiddles) visible; previous iteration's staging retired
@@ -925,8 +1152,10 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(bsrc + i) : "memory");
                 }
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
-                if (overlap && tile + 1 < tile_end)
-                    load_tile_async(s_tile, src, len, (long long)(t0 + TT) * it.hop - NC, it.hop, NFFT, TT, tid, shift);
+                if (overlap && tile + 1 < tile_end) {
+                    src = item_signal(it, cm, p.audio, p.ladder, tm.head(tile + 1), len);
+                    load_tile_async(s_tile, src, len, (long long)tm.first_frame(tile + 1) * it.hop - NC, it.hop, NFFT, TT, tid, shift);
+                }
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
 #pragma unroll
@@ -944,7 +1173,6 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
 
         // Projection.  The lanes of a group hold consecutive frames, so the stores of one row are already T-contiguous
         // (FL * 4 bytes per row and group): results go straight to global memory.
-#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
         {
             constexpr int LPB = FL / 2;              // lanes per block: every lane owns two consecutive frames
             const int sub2 = tid / LPB, lt2 = tid % LPB;
@@ -954,86 +1182,9 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
                 const int bi = w / NCHUNK, ch = w % NCHUNK;
                 const CqtBlock4 *bl = s_blk + bi;
                 project_block2(bl, s_w + (bl->woff - it.woff0), Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + 2 * lt2, DP, out, T,
-                               t0 + ch * FL + 2 * lt2, p.decibels, s_max, gm2, LPB, lt2 == 0, vec2);
+                               t0 + ch * FL + 2 * lt2, p.decibels, s_max, gm2, LPB, lt2 == 0, vec2, skip, cm->t_max);
             }
         }
-#else
-        for (int w = sub; w < it.nblk * NCHUNK; w += NSUB) {
-            const int bi = w / NCHUNK, ch = w % NCHUNK;
-            const CqtBlock4 *bl = s_blk + bi;
-            const int steps = bl->steps;
-            const float4 *wt = s_w + (bl->woff - it.woff0);
-            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + ch * FL + lt;
-#if AMT_PROJ_PACKED
-            // two rows per packed FFMA2: weights (re0, re1 | im0, im1), (re2, re3 | im2, im3); D broadcast to both halves
-            const float2 z2 = make_float2(0.f, 0.f);
-            float2 re01 = z2, ng01 = z2, ia01 = z2, ib01 = z2, re23 = z2, ng23 = z2, ia23 = z2, ib23 = z2;
-#pragma unroll 4
-            for (int s = 0; s < ((AMT_DBG_SKIP & 1) ? 1 : steps); ++s) {
-                const float2 d = Dp[s * DP];
-                const float4 wa = wt[2 * s], wb = wt[2 * s + 1];
-                const float2 dxx = make_float2(d.x, d.x), dyy = make_float2(d.y, d.y);
-                re01 = ffma2(make_float2(wa.x, wa.y), dxx, re01);
-                ng01 = ffma2(make_float2(wa.z, wa.w), dyy, ng01);
-                ia01 = ffma2(make_float2(wa.x, wa.y), dyy, ia01);
-                ib01 = ffma2(make_float2(wa.z, wa.w), dxx, ib01);
-                re23 = ffma2(make_float2(wb.x, wb.y), dxx, re23);
-                ng23 = ffma2(make_float2(wb.z, wb.w), dyy, ng23);
-                ia23 = ffma2(make_float2(wb.x, wb.y), dyy, ia23);
-                ib23 = ffma2(make_float2(wb.z, wb.w), dxx, ib23);
-            }
-            const float2 a0 = make_float2(re01.x - ng01.x, ia01.x + ib01.x), a1 = make_float2(re01.y - ng01.y, ia01.y + ib01.y);
-            const float2 a2 = make_float2(re23.x - ng23.x, ia23.x + ib23.x), a3 = make_float2(re23.y - ng23.y, ia23.y + ib23.y);
-#else
-            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-#pragma unroll 4
-            for (int s = 0; s < ((AMT_DBG_SKIP & 1) ? 1 : steps); ++s) {
-                const float2 d = Dp[s * DP];
-                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
-                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
-                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
-                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
-                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
-                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
-                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
-                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
-                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
-            }
-#endif
-            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
-                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
-            const int t = t0 + ch * FL + lt;
-            const bool live = t < T;
-            if (live) {
-                // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
-                float v[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) v[r] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-                float *ot = out + t;
-                const int ndst = bl->ndst;
-                for (int d = 0; d < ndst; ++d) {
-                    const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
-                    if (off.x >= 0) ot[(long long)off.x * T] = v[0];
-                    if (off.y >= 0) ot[(long long)off.y * T] = v[1];
-                    if (off.z >= 0) ot[(long long)off.z * T] = v[2];
-                    if (off.w >= 0) ot[(long long)off.w * T] = v[3];
-                }
-            }
-            if (p.decibels) {
-                // per-(clip, harmonic) maximum: publish only when some frame of the group exceeds what the CTA already holds
-                // (s_max only grows, so a stale read merely publishes once more)
-                float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
-                int have = s_max[bl->chan[0]];
-                for (int d = 1; d < bl->ndst; ++d) have = min(have, s_max[bl->chan[d]]);
-                if (__any_sync(gmask, __float_as_int(vmax) > have)) {
-#pragma unroll
-                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                    if (lt == 0)
-                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
-                }
-            }
-        }
-#endif
         // no barrier here: the next iteration's top-of-loop barrier orders these reads before the next FFT's scratch writes
     }
     __syncthreads();
@@ -1077,6 +1228,7 @@ struct SlideParams {
     const CqtBlock4 *blocks;
     const float4 *weights4;
     int C, decibels, w_off, blk_off, x_off;
+    unsigned alt_mask;
     int idx[kSlideMaxItems];
     const float2 *tw2[kSlideMaxItems];
 };
@@ -1093,14 +1245,20 @@ __device__ __forceinline__ float2 tw_full(const float2 *__restrict__ tw2, int e,
 
 template <int H>
 __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &it, const float2 *__restrict__ tw2,
-                                          const ClipMeta *cm, int t0, int Tt, float *s_reg, int *s_max) {
+                                          const ClipMeta *cm, int t0, int tend, int Tt, float *s_reg, int *s_max) {
     constexpr int FL = kSlideFL, DP = kSlideDP, HP = (H + 1) / 2;
+    // An error of P scales the whole increment of a frame (hop samples of the FULL signal), so it matters most where the hop is
+    // large: measured on the HCQT, hop 16 / 8 with a re-seed every 8 frames were the least accurate items of the plan (9e-4 dB
+    // on bins 60 dB down); re-seeding from the exact table costs one cached load per frame against 4 hop flops.
+    constexpr int RESEED = (16 / H) < 1 ? 1 : (16 / H) > AMT_SLIDE_RESEED ? AMT_SLIDE_RESEED : (16 / H);
     const int tid = threadIdx.x, NT = blockDim.x;
     const int N = it.nfft, NC = N >> 1, Q = N / H;
     const int kb = it.kmax - it.kmin + 1;
     const bool active = tid < kb;
     const int k = it.kmin + tid;
     const int T = cm->T;
+    // the shared copy of exact-ladder rows skips their first and last frames (chunk-uniform: both bounds are multiples of 32)
+    const int sk_th = it.alt ? 0 : cm->alt_th[it.level], sk_t0 = it.alt ? 0x7fffffff : cm->alt_t0[it.level];
     float2 *Dbuf = reinterpret_cast<float2 *>(s_reg);
     const float4 *s_w = reinterpret_cast<const float4 *>(s_reg + p.w_off);
     const CqtBlock4 *s_blk = reinterpret_cast<const CqtBlock4 *>(s_reg + p.blk_off);
@@ -1153,7 +1311,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     if (active) {
 #pragma unroll 2
         for (int u = 0; u < Q; ++u) {
-            if ((u & (AMT_SLIDE_RESEED - 1)) == 0) P = seed(t0 - Q + u);
+            if ((u & (RESEED - 1)) == 0) P = seed(t0 - Q + u);
             step(s_x + u * H);
         }
     }
@@ -1170,20 +1328,18 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     __syncthreads();
 
     float *out = p.out + cm->out_off;
-    const int sub = tid / FL, lt = tid % FL, NSUB = NT / FL;
-    const unsigned gmask = FL == 32 ? 0xffffffffu : (((1u << FL) - 1u) << (((tid & 31) / FL) * FL));   // lanes of this frame group
-    for (int c0 = 0; c0 < Tt && t0 + c0 < T; c0 += FL) {
+    for (int c0 = 0; c0 < Tt && t0 + c0 < tend; c0 += FL) {
+        const unsigned skip = (t0 + c0 < sk_th || t0 + c0 >= sk_t0) ? p.alt_mask : 0u;
         if (active) {
             float2 *dp = Dbuf + tid * DP;
 #pragma unroll 4
             for (int f = 0; f < FL; ++f) {
-                if ((f & (AMT_SLIDE_RESEED - 1)) == 0) P = seed(t0 + c0 + f);
+                if ((f & (RESEED - 1)) == 0) P = seed(t0 + c0 + f);
                 dp[f] = make_float2(fmaf(P.x, B.x, P.y * B.y), fmaf(P.x, B.y, -P.y * B.x));   // conj(P) * B
                 step(s_x + (c0 + f) * H);
             }
         }
         __syncthreads();
-#if AMT_PROJ_FPL == 2 && AMT_PROJ_PACKED
         {
             constexpr int LPB = FL / 2;
             const int sub2 = tid / LPB, lt2 = tid % LPB;
@@ -1192,84 +1348,9 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
             for (int w = sub2; w < it.nblk; w += NT / LPB) {
                 const CqtBlock4 *bl = s_blk + w;
                 project_block2(bl, s_w + (bl->woff - it.woff0), Dbuf + (bl->col0 - it.kmin) * DP + 2 * lt2, DP, out, T, t0 + c0 + 2 * lt2,
-                               p.decibels, s_max, gm2, LPB, lt2 == 0, vec2);
+                               p.decibels, s_max, gm2, LPB, lt2 == 0, vec2, skip, cm->t_max);
             }
         }
-#else
-        // projection of the chunk: same blocked form as cqt_kernel (lanes along frames, 4 rows per block, packed row pairs)
-        for (int w = sub; w < it.nblk; w += NSUB) {
-            const CqtBlock4 *bl = s_blk + w;
-            const int steps = bl->steps;
-            const float4 *wt = s_w + (bl->woff - it.woff0);
-            const float2 *Dp = Dbuf + (bl->col0 - it.kmin) * DP + lt;
-            float2 a0, a1, a2, a3;
-#if AMT_PROJ_PACKED
-            const float2 z2 = make_float2(0.f, 0.f);
-            float2 re01 = z2, ng01 = z2, ia01 = z2, ib01 = z2, re23 = z2, ng23 = z2, ia23 = z2, ib23 = z2;
-#pragma unroll 4
-            for (int s = 0; s < steps; ++s) {
-                const float2 d = Dp[s * DP];
-                const float4 wa = wt[2 * s], wb = wt[2 * s + 1];
-                const float2 dxx = make_float2(d.x, d.x), dyy = make_float2(d.y, d.y);
-                re01 = ffma2(make_float2(wa.x, wa.y), dxx, re01);
-                ng01 = ffma2(make_float2(wa.z, wa.w), dyy, ng01);
-                ia01 = ffma2(make_float2(wa.x, wa.y), dyy, ia01);
-                ib01 = ffma2(make_float2(wa.z, wa.w), dxx, ib01);
-                re23 = ffma2(make_float2(wb.x, wb.y), dxx, re23);
-                ng23 = ffma2(make_float2(wb.z, wb.w), dyy, ng23);
-                ia23 = ffma2(make_float2(wb.x, wb.y), dyy, ia23);
-                ib23 = ffma2(make_float2(wb.z, wb.w), dxx, ib23);
-            }
-            a0 = make_float2(re01.x - ng01.x, ia01.x + ib01.x); a1 = make_float2(re01.y - ng01.y, ia01.y + ib01.y);
-            a2 = make_float2(re23.x - ng23.x, ia23.x + ib23.x); a3 = make_float2(re23.y - ng23.y, ia23.y + ib23.y);
-#else
-            a0 = a1 = a2 = a3 = make_float2(0.f, 0.f);
-#pragma unroll 4
-            for (int s = 0; s < steps; ++s) {
-                const float2 d = Dp[s * DP];
-                const float4 w01 = wt[2 * s], w23 = wt[2 * s + 1];
-                a0.x = fmaf(w01.x, d.x, a0.x); a0.x = fmaf(-w01.y, d.y, a0.x);
-                a0.y = fmaf(w01.x, d.y, a0.y); a0.y = fmaf(w01.y, d.x, a0.y);
-                a1.x = fmaf(w01.z, d.x, a1.x); a1.x = fmaf(-w01.w, d.y, a1.x);
-                a1.y = fmaf(w01.z, d.y, a1.y); a1.y = fmaf(w01.w, d.x, a1.y);
-                a2.x = fmaf(w23.x, d.x, a2.x); a2.x = fmaf(-w23.y, d.y, a2.x);
-                a2.y = fmaf(w23.x, d.y, a2.y); a2.y = fmaf(w23.y, d.x, a2.y);
-                a3.x = fmaf(w23.z, d.x, a3.x); a3.x = fmaf(-w23.w, d.y, a3.x);
-                a3.y = fmaf(w23.z, d.y, a3.y); a3.y = fmaf(w23.w, d.x, a3.y);
-            }
-#endif
-            const float pw[4] = {fmaf(a0.x, a0.x, a0.y * a0.y) * bl->inv[0], fmaf(a1.x, a1.x, a1.y * a1.y) * bl->inv[1],
-                                 fmaf(a2.x, a2.x, a2.y * a2.y) * bl->inv[2], fmaf(a3.x, a3.x, a3.y * a3.y) * bl->inv[3]};
-            const int t = t0 + c0 + lt;
-            const bool live = t < T;
-            if (live) {
-                // rows shared by several harmonics are stored to each of them (one 16-byte descriptor load per destination)
-                float v[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) v[r] = p.decibels ? db10(fmaxf(1e-10f, pw[r])) : sqrtf(pw[r]);
-                float *ot = out + t;
-                const int ndst = bl->ndst;
-                for (int d = 0; d < ndst; ++d) {
-                    const int4 off = *reinterpret_cast<const int4 *>(bl->off[d]);
-                    if (off.x >= 0) ot[(long long)off.x * T] = v[0];
-                    if (off.y >= 0) ot[(long long)off.y * T] = v[1];
-                    if (off.z >= 0) ot[(long long)off.z * T] = v[2];
-                    if (off.w >= 0) ot[(long long)off.w * T] = v[3];
-                }
-            }
-            if (p.decibels) {
-                float vmax = live ? fmaxf(fmaxf(pw[0], pw[1]), fmaxf(pw[2], pw[3])) : 0.f;
-                int have = s_max[bl->chan[0]];
-                for (int d = 1; d < bl->ndst; ++d) have = min(have, s_max[bl->chan[d]]);
-                if (__any_sync(gmask, __float_as_int(vmax) > have)) {
-#pragma unroll
-                    for (int o = FL / 2; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(gmask, vmax, o));
-                    if (lt == 0)
-                        for (int d = 0; d < bl->ndst; ++d) atomicMax(&s_max[bl->chan[d]], __float_as_int(vmax));
-                }
-            }
-        }
-#endif
         __syncthreads();
     }
 }
@@ -1281,15 +1362,18 @@ __global__ void __launch_bounds__(kThreads, AMT_SLIDE_CTAS) cqt_slide_kernel(con
     const CqtItem it = p.items[p.idx[blockIdx.z]];
     const float2 *tw2 = p.tw2[blockIdx.z];
     const ClipMeta *cm = p.meta + blockIdx.y;
-    const int T = cm->T, Tt = slide_tile_frames(it.hop);
-    const int t0 = blockIdx.x * Tt;
-    if (t0 >= T) return;
+    const int Tall = cm->T_all, Tt = slide_tile_frames(it.hop);
+    // tiles of Tt frames; an exact-ladder item covers the first and the last frames of its level only (TileMap)
+    const TileMap tm(it, cm, Tall, Tt);
+    if ((int)blockIdx.x >= tm.ntiles) return;
+    const bool head = tm.head(blockIdx.x);
+    const int t0 = tm.first_frame(blockIdx.x), tend = tm.frame_end(blockIdx.x, Tall);
     if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
     {
         // the tile's samples [t0 hop - N/2, (t0 + Tt) hop + N/2), zero outside the level signal (16-byte cp.async with zero
         // fill: the start is a multiple of 4 samples), and the item's weights and block descriptors
-        const float *src = (it.level == 0 ? p.audio : p.ladder) + cm->lvl_off[it.level];
-        const long long len = cm->lvl_len[it.level];
+        long long len;
+        const float *src = item_signal(it, cm, p.audio, p.ladder, head, len);
         const long long j0 = (long long)t0 * it.hop - it.nfft / 2;
         const int nvec = (Tt * it.hop + it.nfft) >> 2;
         float *s_x = smem + p.x_off;
@@ -1319,11 +1403,11 @@ __global__ void __launch_bounds__(kThreads, AMT_SLIDE_CTAS) cqt_slide_kernel(con
     }
     __syncthreads();
     switch (it.hop) {
-        case 16: slide_run<16>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
-        case 8: slide_run<8>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
-        case 4: slide_run<4>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
-        case 2: slide_run<2>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
-        default: slide_run<1>(p, it, tw2, cm, t0, Tt, smem, s_max); break;
+        case 16: slide_run<16>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
+        case 8: slide_run<8>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
+        case 4: slide_run<4>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
+        case 2: slide_run<2>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
+        default: slide_run<1>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
     }
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
@@ -1344,12 +1428,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ClipMeta *cm = p.meta + blockIdx.y;
-    const int T = cm->T;
-    const int t0 = blockIdx.x * TT;
-    if (t0 >= T) return;
+    const int T = cm->T, Tall = cm->T_all;
     const CqtItem it = p.items[blockIdx.z];
+    const TileMap tm(it, cm, Tall, TT);
+    if ((int)blockIdx.x >= tm.ntiles) return;
+    const int t0 = tm.first_frame(blockIdx.x), tend = tm.frame_end(blockIdx.x, Tall);
     if (tid < AMTFEAT_MAX_HARMONICS) s_max[tid] = 0;
-    cqt_fft_phase<NC>(p, it, cm, t0, s_tw1, s_tw2, s_scr, s_tile);
+    cqt_fft_phase<NC>(p, it, cm, t0, tm.head(blockIdx.x), s_tw1, s_tw2, s_scr, s_tile);
 
     float2 *scr = reinterpret_cast<float2 *>(s_scr) + warp * WP2;
     const int kb = it.kmax_true - it.kmin + 1;
@@ -1405,10 +1490,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
                 }
             }
             float vmax = 0.f;
+            const bool alt_row = ((p.alt_mask >> row.chan) & 1u) != 0;
+            const int tlim = min(tend, p.decibels ? cm->t_max[row.chan] : T);
 #pragma unroll
             for (int f = 0; f < 8; ++f) {
                 const float pw = fmaf(acc[f].x, acc[f].x, acc[f].y * acc[f].y) * row.inv_len;
-                if (t0 + ch * 8 + f < T) vmax = fmaxf(vmax, pw);
+                const int t = t0 + ch * 8 + f;
+                if (t < tlim && !(alt_row && tm.skip(t, 1u))) vmax = fmaxf(vmax, pw);
                 s_stage[rl * (TT + 1) + ch * 8 + f] = p.decibels ? db10(fmaxf(1e-10f, pw)) : sqrtf(pw);
             }
             if (p.decibels) atomicMax(&s_max[row.chan], __float_as_int(vmax));
@@ -1416,9 +1504,11 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
         __syncthreads();
         for (int idx = tid; idx < nr * TT; idx += kThreads) {
             const int t = idx % TT, rl = idx / TT;
-            if (t0 + t < T) {
+            if (t0 + t < min(T, tend)) {
                 const CqtRow *row = p.rows + it.row0 + rc + rl;
-                out[((long long)__ldg(&row->chan) * p.F + __ldg(&row->bin)) * T + t0 + t] = s_stage[rl * (TT + 1) + t];
+                const int chan = __ldg(&row->chan);
+                if (!(((p.alt_mask >> chan) & 1u) && tm.skip(t0 + t, 1u)))
+                    out[((long long)chan * p.F + __ldg(&row->bin)) * T + t0 + t] = s_stage[rl * (TT + 1) + t];
             }
         }
         __syncthreads();
@@ -1475,15 +1565,37 @@ template <int NC> static int set_attrs() {
     return AMTFEAT_OK;
 }
 
+// Makes the plan's device current for the duration of a call and restores the caller's device afterwards: creating,
+// using or destroying a plan for cuda:k must not move the calling thread to cuda:k.
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    explicit DeviceGuard(int device) {
+        if (device < 0 || cudaGetDevice(&prev) != cudaSuccess) return;
+        if (prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
 int upload_plan(Plan &p) {
-    AMT_CUDA(cudaSetDevice(p.device));
+    DeviceGuard guard(p.device);
+    {
+        int cur = -1;
+        AMT_CUDA(cudaGetDevice(&cur));
+        if (cur != p.device) AMT_CUDA(cudaSetDevice(p.device));   // reports an invalid ordinal
+    }
     if (is_vqt_kind_cfg(p.cfg.kind)) {
         // highest priority: the ladder's few CTAs take the next free SM slots instead of queueing behind a projection grid
         int prio_lo = 0, prio_hi = 0;
         AMT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        cudaStream_t side;
-        AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
-        p.side_stream = side;
+        for (int sl = 0; sl < Plan::kCallSlots; ++sl) {
+            cudaStream_t side;
+            AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
+            p.side_stream[sl] = side;
+            for (void *&e : p.call_events[sl]) AMT_CUDA(cudaEventCreateWithFlags(reinterpret_cast<cudaEvent_t *>(&e), cudaEventDisableTiming));
+        }
     }
     int rc;
     if ((rc = set_attrs<1024>()) || (rc = set_attrs<512>()) || (rc = set_attrs<256>()) || (rc = set_attrs<128>()) ||
@@ -1492,6 +1604,7 @@ int upload_plan(Plan &p) {
         return rc;
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(decimate_fft64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(cqt_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
@@ -1499,7 +1612,12 @@ int upload_plan(Plan &p) {
     if ((rc = upload_vec(p, p.mel_off, &p.d_mel_off))) return rc;
     if ((rc = upload_vec(p, p.mel_w, &p.d_mel_w))) return rc;
     if ((rc = upload_vec(p, p.taps, &p.d_taps))) return rc;
+    if ((rc = upload_vec(p, p.taps64, &p.d_taps64))) return rc;
     if ((rc = upload_vec(p, p.decim_hh, &p.d_decim_hh))) return rc;
+    if ((rc = upload_vec(p, p.decim_h64, &p.d_decim_h64))) return rc;
+    if ((rc = upload_vec(p, p.decim_tw64, &p.d_decim_tw64))) return rc;
+    for (AltLadder &al : p.alts)
+        if ((rc = upload_vec(p, al.taps, &al.d_taps))) return rc;
     if ((rc = upload_vec(p, p.rows, &p.d_rows))) return rc;
     if ((rc = upload_vec(p, p.weights, &p.d_weights))) return rc;
     if ((rc = upload_vec(p, p.blocks, &p.d_blocks))) return rc;
@@ -1518,12 +1636,17 @@ int upload_plan(Plan &p) {
 
 // Sums the recorded event pairs per kernel name into `json` and clears the records.
 int profile_read(const Plan &p, std::string &json) {
+    DeviceGuard guard(p.device);
+    std::lock_guard<std::mutex> lock(p.call_mu);
     std::map<std::string, std::pair<double, int>> acc;
+    int rc = AMTFEAT_OK;
     for (auto &r : p.prof) {
         cudaEvent_t e0 = (cudaEvent_t)r.e0, e1 = (cudaEvent_t)r.e1;
-        AMT_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
-        AMT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) {
+            set_error("profile_read: an event pair could not be read");
+            rc = AMTFEAT_ERR_CUDA;
+        }
         acc[r.name].first += ms;
         acc[r.name].second += 1;
         cudaEventDestroy(e0);
@@ -1539,31 +1662,38 @@ int profile_read(const Plan &p, std::string &json) {
         first = false;
     }
     json += "}";
-    return AMTFEAT_OK;
+    return rc;
 }
 
 void free_plan_device(Plan &p) {
-    if (p.device >= 0 && p.side_stream) {
-        cudaSetDevice(p.device);
-        cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream));
-        cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream));
-        p.side_stream = nullptr;
+    if (p.device < 0) return;
+    DeviceGuard guard(p.device);
+    for (int sl = 0; sl < Plan::kCallSlots; ++sl) {
+        if (p.side_stream[sl]) {
+            cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream[sl]));
+            cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream[sl]));
+            p.side_stream[sl] = nullptr;
+        }
+        for (void *&e : p.call_events[sl])
+            if (e) { cudaEventDestroy(reinterpret_cast<cudaEvent_t>(e)); e = nullptr; }
     }
-    if (p.device >= 0 && p.meta_ring) {
-        cudaSetDevice(p.device);
+    for (auto &r : p.prof) {
+        cudaEventDestroy((cudaEvent_t)r.e0);
+        cudaEventDestroy((cudaEvent_t)r.e1);
+    }
+    p.prof.clear();
+    if (p.meta_ring) {
         for (void *&e : p.meta_events)
             if (e) { cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(e)); cudaEventDestroy(reinterpret_cast<cudaEvent_t>(e)); e = nullptr; }
         cudaFreeHost(p.meta_ring);
         p.meta_ring = nullptr;
         p.meta_slot_bytes = 0;
     }
-    if (p.device >= 0 && !p.d_allocs.empty()) {
-        cudaSetDevice(p.device);
-        for (void *d : p.d_allocs) cudaFree(d);
-    }
+    for (void *d : p.d_allocs) cudaFree(d);
     p.d_allocs.clear();
 }
 
+// Event pair around one launch (amtfeat_profile_*): recorded under Plan::call_mu, like everything process() enqueues.
 struct ProfScope {
     const Plan &p;
     cudaStream_t st;
@@ -1583,9 +1713,26 @@ struct ProfScope {
 
 static bool is_vqt_kind(const Plan &p) { return p.cfg.kind == AMTFEAT_VQT || p.cfg.kind == AMTFEAT_HVQT; }
 
-// workspace: [ClipMeta x B][maxbuf float x B*C][ladder levels 1..n_levels-1]
+// Frames of one clip: T stored, T_all computed (the dB maximum of a harmonic runs over its own, untrimmed VQT: hvqt.py:123-128
+// converts every harmonic to dB before trimming it to the common frame count).
+static bool clip_frames(const Plan &p, int64_t n, ClipMeta &cm) {
+    const int64_t T = output_frames(p, n);
+    if (T < 0) return false;
+    cm.T = cm.T_all = (int32_t)T;
+    for (int c = 0; c < AMTFEAT_MAX_HARMONICS; ++c) cm.t_max[c] = (int32_t)T;
+    if (p.cfg.kind == AMTFEAT_HVQT && p.cfg.decibels && T > 0) {
+        for (size_t h = 0; h < p.harm.size(); ++h) {
+            cm.t_max[h] = (int32_t)std::max<int64_t>(T, harmonic_frames(p, (int)h, n));
+            cm.T_all = std::max(cm.T_all, cm.t_max[h]);
+        }
+    }
+    return true;
+}
+
+// workspace: [ClipMeta x B][maxbuf float x B*C][ladder levels 1..n_levels-1][tails of the exact ladders]
 struct WsLayout {
     size_t meta_off = 0, max_off = 0, ladder_off = 0, total = 0;
+    bool ok = true;
 };
 static WsLayout ws_layout(const Plan &p, int batch, const int64_t *n, std::vector<ClipMeta> *metas) {
     WsLayout w;
@@ -1593,18 +1740,47 @@ static WsLayout ws_layout(const Plan &p, int batch, const int64_t *n, std::vecto
     w.max_off = align_up((size_t)batch * sizeof(ClipMeta), 256);
     w.ladder_off = align_up(w.max_off + (size_t)batch * p.C * sizeof(float), 256);
     size_t ladder_elems = 0;
-    if (metas) metas->assign(batch, ClipMeta{});
+    std::vector<ClipMeta> local;
+    std::vector<ClipMeta> &ms = metas ? *metas : local;
+    ms.assign(batch, ClipMeta{});
+    for (int b = 0; b < batch; ++b) {
+        if (!clip_frames(p, n[b], ms[b])) w.ok = false;
+        for (int l = 0; l < kMaxLevels; ++l) {
+            ms[b].alt_t0[l] = INT32_MAX;
+            ms[b].alt_th[l] = 0;
+            for (int a = 0; a < kMaxAlt; ++a) { ms[b].alt_first[a][l] = -1; ms[b].alt_hlen[a][l] = 0; }
+        }
+    }
     if (is_vqt_kind(p)) {
+        for (int b = 0; b < batch; ++b) level_lengths(p, n[b], ms[b].lvl_len);
         for (int l = 1; l < p.n_levels; ++l)
             for (int b = 0; b < batch; ++b) {
-                int32_t len[kMaxLevels];
-                level_lengths(p, n[b], len);
-                if (metas) {
-                    (*metas)[b].lvl_off[l] = (int64_t)ladder_elems;
-                    (*metas)[b].lvl_len[l] = len[l];
-                }
-                ladder_elems += align_up((size_t)len[l], 4);
+                ms[b].lvl_off[l] = (int64_t)ladder_elems;
+                ladder_elems += align_up((size_t)ms[b].lvl_len[l], 4);
             }
+        if (!p.alts.empty()) {
+            TailLayout tl;
+            for (int b = 0; b < batch; ++b) {
+                clip_tail_layout(p, n[b], ms[b].T_all, tl);
+                for (int l = 0; l < kMaxLevels; ++l) { ms[b].alt_t0[l] = tl.t0[l]; ms[b].alt_th[l] = tl.th[l]; }
+                for (size_t a = 0; a < p.alts.size(); ++a)
+                    for (int l = 0; l < kMaxLevels; ++l) {
+                        ms[b].alt_first[a][l] = tl.first[a][l];
+                        if (tl.first[a][l] >= 0) {
+                            ms[b].alt_off[a][l] = (int64_t)ladder_elems - tl.first[a][l];   // virtual: sample m lives at alt_off + m
+                            ladder_elems += align_up((size_t)tl.count[a][l], 4) + 4;
+                        }
+                        if (tl.hlen[a][l] > 0) {
+                            ms[b].alt_hoff[a][l] = (int64_t)ladder_elems;
+                            ms[b].alt_hlen[a][l] = tl.hlen[a][l];
+                            ladder_elems += align_up((size_t)tl.hlen[a][l], 4) + 4;
+                        } else if (tl.hlen[a][l] < 0) {      // the tail piece holds the whole level (first == 0)
+                            ms[b].alt_hoff[a][l] = ms[b].alt_off[a][l];
+                            ms[b].alt_hlen[a][l] = ms[b].lvl_len[l];
+                        }
+                    }
+            }
+        }
     }
     w.total = w.ladder_off + ladder_elems * sizeof(float) + 256;
     return w;
@@ -1612,30 +1788,38 @@ static WsLayout ws_layout(const Plan &p, int batch, const int64_t *n, std::vecto
 
 size_t workspace_bytes(const Plan &p, int batch, const int64_t *n) { return ws_layout(p, batch, n, nullptr).total; }
 
+static int slide_class(const CqtItem &it) {
+    const int kb = it.kmax - it.kmin + 1;
+    return AMT_SLIDE_SPLIT == 0 ? 0 : AMT_SLIDE_SPLIT == 1 ? (kb <= 128 ? 0 : 1) : (kb + 31) / 32;
+}
+
+// Launch classes of the VQT-family items: 0 = level 0 | 1 = levels 1 .. AMT_MID_LEVEL | 2 = deeper (FFT per frame, caller's stream,
+// each class waits only for the ladder levels it reads), 3 = sliding DFT (side stream), 4 / 5 = exact-ladder tails (FFT per
+// frame / sliding DFT, side stream).
+static int item_class(const Plan &p, const CqtItem &it, bool overlap) {
+    const bool slide = !p.slide_off && is_slide_item(it);
+    if (it.alt) return slide ? 5 : 4;
+    if (slide) return 3;
+    return !overlap ? 0 : it.level == 0 ? 0 : it.level <= AMT_MID_LEVEL ? 1 : 2;
+}
+
 int launch_count(const Plan &p, int batch, const int64_t *n) {
     (void)batch;
     (void)n;
     int k = 0;
     if (is_vqt_kind(p)) {
         k += p.n_levels - 1;
-        // one projection launch per run of equal n_fft and equal ladder-depth class (see process())
-        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream != nullptr && p.n_levels > 1;
-        int last = -1, last_cls = -1, nslide = 0;
+        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream[0] != nullptr && p.n_levels > 1;
+        // one FFT-per-frame launch per run of equal n_fft and equal class; one sliding-DFT launch per CTA-size class
+        int last = -1, last_cls = -1;
+        std::map<std::pair<int, int>, int> sl;
         for (const CqtItem &it : p.items) {
-            if (!p.slide_off && is_slide_item(it)) { ++nslide; last = -1; continue; }
-            const int cls = !overlap ? 0 : it.level == 0 ? 0 : it.level <= AMT_MID_LEVEL ? 1 : 2;
+            const int cls = item_class(p, it, overlap);
+            if (cls == 3 || cls == 5) { ++sl[{cls, slide_class(it)}]; last = -1; continue; }
             if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
         }
-        (void)nslide;
-        {
-            std::map<int, int> classes;
-            for (const CqtItem &it : p.items)
-                if (!p.slide_off && is_slide_item(it)) {
-                    const int kb = it.kmax - it.kmin + 1;
-                    ++classes[AMT_SLIDE_SPLIT == 0 ? 0 : AMT_SLIDE_SPLIT == 1 ? (kb <= 128 ? 0 : 1) : (kb + 31) / 32];
-                }
-            for (auto &kv : classes) k += (kv.second + kSlideMaxItems - 1) / kSlideMaxItems;
-        }
+        for (auto &kv : sl) k += (kv.second + kSlideMaxItems - 1) / kSlideMaxItems;
+        for (const AltLadder &al : p.alts) { (void)al; k += 2 * p.n_oct; }   // head + tail piece of every level of an exact ladder
     } else {
         k += 1;
     }
@@ -1665,8 +1849,10 @@ static int launch_stft(const Plan &p, const StftParams &sp_in, int batch, int ma
     return AMTFEAT_OK;
 }
 
+// FFT-per-frame launch over the items [item0, item0 + nitems) (one n_fft, one class); `frames` = most frames any
+// (clip, item) of the launch computes (T_all, or the length of the tail for exact-ladder items).
 template <int NC>
-static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int batch, int maxT, cudaStream_t st) {
+static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int batch, int frames, bool tail, cudaStream_t st) {
     using L = FftLayout<NC>;
     const int TT = kWarpsPerCta * L::G;
     int maxhop = 0, maxrows = 0, maxblk = 0, maxkb = 0;
@@ -1681,9 +1867,9 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     const FftTables &ft = p.fft.at(NC);
     cp.tw1 = reinterpret_cast<const float2 *>(ft.d_tw1);
     cp.tw2 = reinterpret_cast<const float2 *>(ft.d_tw2);
-    const int ntiles = (maxT + TT - 1) / TT;
+    const int ntiles = (frames + TT - 1) / TT;
     dim3 grid(ntiles, batch, nitems);
-    static const std::string nm = "cqt_kernel_nfft" + std::to_string(2 * NC);
+    const std::string nm = tail ? std::string("tail_cqt_kernel") : "cqt_kernel_nfft" + std::to_string(2 * NC);
     size_t smem;
     if (cqt_use_blocks<NC>()) {
         // phase B reuses the retired FFT scratch: Dbuf | the item's weights | its block descriptors.  The audio
@@ -1722,13 +1908,29 @@ static int launch_cqt(const Plan &p, CqtParams cp, int item0, int nitems, int ba
     return AMTFEAT_OK;
 }
 
-// Sliding-DFT launch over the items `idx` (all of them pass is_slide_item).
-static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<int> &idx, int batch, int maxT, cudaStream_t st) {
+static int launch_cqt_nc(const Plan &p, const CqtParams &cp, int NC, int item0, int nitems, int batch, int frames, bool tail, cudaStream_t st) {
+    switch (NC) {
+        case 1024: return launch_cqt<1024>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 512: return launch_cqt<512>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 256: return launch_cqt<256>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 128: return launch_cqt<128>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 64: return launch_cqt<64>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 32: return launch_cqt<32>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 16: return launch_cqt<16>(p, cp, item0, nitems, batch, frames, tail, st);
+        case 8: return launch_cqt<8>(p, cp, item0, nitems, batch, frames, tail, st);
+        default: return launch_cqt<4>(p, cp, item0, nitems, batch, frames, tail, st);
+    }
+}
+
+// Sliding-DFT launch over the items `idx` (all of them pass is_slide_item); frames[i] = most frames a clip computes of item idx[i].
+static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<int> &idx, const std::vector<int> &frames, int batch,
+                        bool tail, cudaStream_t st) {
     for (size_t i0 = 0; i0 < idx.size(); i0 += kSlideMaxItems) {
         const int cnt = (int)std::min<size_t>(kSlideMaxItems, idx.size() - i0);
         SlideParams sp{};
         sp.audio = cp.audio; sp.ladder = cp.ladder; sp.out = cp.out; sp.meta = cp.meta; sp.maxbuf = cp.maxbuf;
         sp.items = p.d_items; sp.blocks = cp.blocks; sp.weights4 = cp.weights4; sp.C = cp.C; sp.decibels = cp.decibels;
+        sp.alt_mask = cp.alt_mask;
         int maxkb = 0, maxw = 0, maxblk = 0, maxx = 0, tiles = 0;
         for (int i = 0; i < cnt; ++i) {
             const CqtItem &it = p.items[idx[i0 + i]];
@@ -1739,8 +1941,9 @@ static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<in
             maxw = std::max(maxw, it.wcount);
             maxblk = std::max(maxblk, it.nblk);
             maxx = std::max(maxx, Tt * it.hop + it.nfft);
-            tiles = std::max(tiles, (maxT + Tt - 1) / Tt);
+            tiles = std::max(tiles, (frames[i0 + i] + Tt - 1) / Tt);
         }
+        if (tiles == 0) continue;
         const int threads = (maxkb + 31) / 32 * 32;
         sp.w_off = (maxkb * kSlideDP * 2 + 3) / 4 * 4;
         sp.blk_off = sp.w_off + maxw * 4;
@@ -1748,35 +1951,52 @@ static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<in
         const size_t smem = (size_t)(sp.x_off + maxx + 8) * sizeof(float);
         if (smem > 226 * 1024) { set_error("sliding-DFT tile does not fit in shared memory"); return AMTFEAT_ERR_INVALID; }
         dim3 grid(tiles, batch, cnt);
-        ProfScope ps(p, "cqt_slide_kernel", st);
+        ProfScope ps(p, tail ? "tail_slide_kernel" : "cqt_slide_kernel", st);
         cqt_slide_kernel<<<grid, threads, smem, st>>>(sp);
         AMT_CUDA(cudaGetLastError());
     }
     return AMTFEAT_OK;
 }
 
+// Joins the side stream back into the caller's stream on every exit path of the VQT family (error returns included), so
+// that no call leaves work dangling behind the caller's back.
+struct SideJoin {
+    cudaStream_t st, side;
+    cudaEvent_t ev;
+    bool armed = false;
+    ~SideJoin() {
+        if (!armed) return;
+        cudaEventRecord(ev, side);
+        cudaStreamWaitEvent(st, ev, 0);
+    }
+};
+
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
             int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream) {
     if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
     if (batch <= 0) return AMTFEAT_OK;
+    if ((reinterpret_cast<uintptr_t>(d_audio) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) || (reinterpret_cast<uintptr_t>(d_ws) & 255)) {
+        set_error("d_audio / d_out must be 16-byte aligned and the workspace 256-byte aligned");
+        return AMTFEAT_ERR_INVALID;
+    }
+    DeviceGuard guard(p.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const amtfeat_config &c = p.cfg;
     std::vector<ClipMeta> metas;
     const WsLayout w = ws_layout(p, batch, n, &metas);
+    if (!w.ok) { set_error("input too short for an uncentered frame (n_fft / win_length larger than the padded signal)"); return AMTFEAT_ERR_INVALID; }
     if (ws_bytes < w.total) { set_error("workspace too small"); return AMTFEAT_ERR_WORKSPACE; }
-    int maxT = 0;
+    int maxT = 0, maxTall = 0;
     int64_t maxn = 0;
     for (int b = 0; b < batch; ++b) {
-        const int64_t T = output_frames(p, n[b]);
-        if (T < 0) { set_error("input too short for an uncentered frame (n_fft / win_length larger than the padded signal)"); return AMTFEAT_ERR_INVALID; }
         if (in_off[b] % 4 != 0) { set_error("clip offsets must be multiples of 4 elements"); return AMTFEAT_ERR_INVALID; }
         metas[b].in_off = in_off[b];
         metas[b].lvl_off[0] = in_off[b];
         metas[b].lvl_len[0] = (int32_t)n[b];
         metas[b].n = n[b];
         metas[b].out_off = out_off[b];
-        metas[b].T = (int32_t)T;
-        maxT = std::max<int>(maxT, (int)T);
+        maxT = std::max<int>(maxT, metas[b].T);
+        maxTall = std::max<int>(maxTall, metas[b].T_all);
         maxn = std::max(maxn, n[b]);
     }
     if (maxT == 0) return AMTFEAT_OK;
@@ -1784,10 +2004,12 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
     ClipMeta *d_meta = reinterpret_cast<ClipMeta *>(ws + w.meta_off);
     float *d_max = reinterpret_cast<float *>(ws + w.max_off);
     float *d_ladder = reinterpret_cast<float *>(ws + w.ladder_off);
+    // everything below is enqueued under the plan's call lock: the descriptor ring, the fork / join events of the call slot and
+    // the profiling records are plan state; concurrent callers of one plan serialise their (short) host-side enqueue here
+    std::lock_guard<std::mutex> call_lock(p.call_mu);
     {
         // descriptors go through a pinned ring slot (truly asynchronous copy); a slot is reused once its last copy has completed
         const size_t need = metas.size() * sizeof(ClipMeta);
-        std::lock_guard<std::mutex> lock(p.meta_mu);
         if (need > p.meta_slot_bytes) {
             for (void *&e : p.meta_events) {
                 if (e) AMT_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(e)));
@@ -1847,48 +2069,49 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         AMT_CUDA(cudaGetLastError());
         return AMTFEAT_OK;
     } else {
-        // Decimation ladder (levels 1 .. n_levels-1) on the plan's side stream, CQT launches on the caller's stream.
-        // The deep ladder levels are short and latency-bound (~20 us per launch with the GPU mostly idle), so the
-        // projection launches are cut by ladder depth -- level 0 (needs no ladder), levels 1-2, deeper -- and each class
-        // only waits for the ladder levels it reads: the ladder runs underneath the projection of the shallower levels.
+        // Decimation ladder (levels 1 .. n_levels-1) on one of the plan's side streams, FFT-per-frame launches on the caller's
+        // stream.  The deep ladder levels are short and latency-bound, so the FFT-per-frame launches are cut by ladder depth
+        // (item_class) and each class only waits for the ladder levels it reads: the ladder runs underneath the projection of
+        // the shallower levels.  The sliding-DFT items and the exact-ladder tails follow the ladder on the side stream.
         const int ntaps = (int)p.taps.size(), D = (ntaps - 1) / 2;
         const int dlen = dec_front_pad(D) + kDecTile + D + 8;
         const int dplen = ((dlen + ((dlen >> 4) << 2)) + 7) & ~3;
         const size_t dsmem = (size_t)(2 * dplen + 2 * dec_jtot(D)) * sizeof(float);
         int64_t len = maxn;
-        const bool fast = !p.decim_hh.empty() && !p.decim_direct;
-        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream != nullptr && p.n_levels > 1;
-        cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream) : st;
+        const int mode = (p.decim_mode == 0 && !p.decim_h64.empty()) ? 0 : (p.decim_mode <= 1 && !p.decim_hh.empty()) ? 1 : 2;
+        const bool overlap = AMT_LADDER_OVERLAP && !p.serial_launch && p.side_stream[0] != nullptr && p.n_levels > 1;
+        const unsigned call_slot = p.call_next++ % Plan::kCallSlots;
+        cudaStream_t lst = overlap ? reinterpret_cast<cudaStream_t>(p.side_stream[call_slot]) : st;
+        cudaEvent_t ev_fork = reinterpret_cast<cudaEvent_t>(p.call_events[call_slot][0]), ev_mid = reinterpret_cast<cudaEvent_t>(p.call_events[call_slot][1]),
+                    ev_all = reinterpret_cast<cudaEvent_t>(p.call_events[call_slot][2]), ev_side = reinterpret_cast<cudaEvent_t>(p.call_events[call_slot][3]);
         constexpr int kMidLevel = AMT_MID_LEVEL;           // classes: level 0 | 1 .. kMidLevel | deeper
-        // items on the sliding-DFT kernel (deep levels) and the deepest level the FFT-per-frame launches read
-        std::vector<int> slide_idx;
+        // the deepest level the FFT-per-frame launches of the caller's stream read
         int max_fft_level = 0;
-        for (size_t i = 0; i < p.items.size(); ++i) {
-            if (!p.slide_off && is_slide_item(p.items[i])) slide_idx.push_back((int)i);
-            else max_fft_level = std::max(max_fft_level, (int)p.items[i].level);
-        }
-#ifndef AMT_SLIDE_SORT
-#define AMT_SLIDE_SORT 1
-#endif
-        // CTAs are handed out in grid order (z slowest): the items with the longest tiles (smallest hop: most frames and the longest
-        // lead-in per tile) go first so that they do not form the tail of the launch
-        if (AMT_SLIDE_SORT)
-            std::stable_sort(slide_idx.begin(), slide_idx.end(), [&](int a, int b) { return p.items[a].hop < p.items[b].hop; });
+        for (const CqtItem &it : p.items)
+            if (item_class(p, it, overlap) <= 2) max_fft_level = std::max(max_fft_level, (int)it.level);
         const int deep_level = std::min(p.n_levels - 1, std::max(max_fft_level, kMidLevel));
-        cudaEvent_t ev_fork = nullptr, ev_mid = nullptr, ev_all = nullptr, ev_side = nullptr;
+        SideJoin join{st, lst, ev_side};
         if (overlap) {
-            AMT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-            AMT_CUDA(cudaEventCreateWithFlags(&ev_mid, cudaEventDisableTiming));
-            AMT_CUDA(cudaEventCreateWithFlags(&ev_all, cudaEventDisableTiming));
-            AMT_CUDA(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming));
             AMT_CUDA(cudaEventRecord(ev_fork, st));        // clip descriptors / cleared maxima are in place
             AMT_CUDA(cudaStreamWaitEvent(lst, ev_fork, 0));
+            join.armed = true;
         }
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
-            // (both forms have a ~20 us latency floor per launch on the short, deep levels: one warp runs three 1024-point
-            // transforms back to back / one thread runs 16 x 389 MACs; mixing the forms per level was measured and is no faster)
-            if (fast) {
+            if (mode == 0) {
+                Dec64Params dp{};
+                dp.audio = d_audio; dp.ladder = d_ladder; dp.meta = d_meta;
+                dp.tw = reinterpret_cast<const double2 *>(p.d_decim_tw64); dp.H = reinterpret_cast<const double2 *>(p.d_decim_h64);
+                dp.level_out = l; dp.D = D; dp.M = 1024 - D;
+                const int64_t npairs = (len + 2 * dp.M - 1) / (2 * dp.M);
+                dp.pairs_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs * batch / (148 * 2 * 2)));
+                const size_t fsmem = (size_t)(1024 + 2 * 2048) * sizeof(double2);
+                dim3 grid((unsigned)((npairs + dp.pairs_per_cta - 1) / dp.pairs_per_cta), batch);
+                ProfScope ps(p, "decimate_fft64_kernel", lst);
+                decimate_fft64_kernel<<<grid, kD64Threads, fsmem, lst>>>(dp);
+            } else if (mode == 1) {
+                // (both float32 forms have a ~20 us latency floor per launch on the short, deep levels: one warp runs three 1024-point
+                // transforms back to back / one thread runs 16 x 389 MACs; mixing the forms per level was measured and is no faster)
                 using L = FftLayout<1024>;
                 DecFftParams dp{};
                 dp.audio = d_audio; dp.ladder = d_ladder; dp.meta = d_meta; dp.hh = reinterpret_cast<const float4 *>(p.d_decim_hh);
@@ -1912,61 +2135,90 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         cp.audio = d_audio; cp.ladder = d_ladder; cp.out = d_out; cp.meta = d_meta; cp.maxbuf = d_max;
         cp.rows = p.d_rows; cp.weights = reinterpret_cast<const float2 *>(p.d_weights);
         cp.blocks = p.d_blocks; cp.weights4 = reinterpret_cast<const float4 *>(p.d_weights4);
-        cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels;
-        // The sliding-DFT items follow the ladder on its (high-priority) stream: their few, long-running CTAs start as soon
-        // as the deep levels exist and run underneath the FFT-per-frame launches of the shallower levels.
-        if (!slide_idx.empty()) {
-            // One launch per CTA-size class (narrow bands first: they hold the longest tiles), so that a narrow band does not carry
-            // the idle warps, registers and shared memory of the widest one while it shares the SMs with the FFT launches.
-            std::map<int, std::vector<int>> classes;
-            for (int i : slide_idx) {
-                const int kb = p.items[i].kmax - p.items[i].kmin + 1;
-                classes[AMT_SLIDE_SPLIT == 0 ? 0 : AMT_SLIDE_SPLIT == 1 ? (kb <= 128 ? 0 : 1) : (kb + 31) / 32].push_back(i);
+        cp.C = p.C; cp.F = p.F; cp.decibels = c.decibels; cp.alt_mask = p.alt_mask;
+        // tiles (of TT frames) an exact-ladder item computes at most, as frames: head tiles + tail tiles, longest clip of the batch
+        auto tail_frames = [&](const CqtItem &it, int TT) {
+            int tiles = 0;
+            for (int b = 0; b < batch; ++b) {
+                const ClipMeta &m = metas[b];
+                int t = (std::min(m.alt_th[it.level], m.T_all) + TT - 1) / TT;
+                if (m.alt_t0[it.level] < m.T_all) t += (m.T_all - m.alt_t0[it.level] + TT - 1) / TT;
+                tiles = std::max(tiles, t);
             }
-            for (auto &kv : classes)
-                if (!rc) rc = launch_slide(p, cp, kv.second, batch, maxT, lst);
-        }
-        if (overlap) AMT_CUDA(cudaEventRecord(ev_side, lst));
-        auto level_class = [&](int level) { return !overlap ? 0 : level == 0 ? 0 : level <= kMidLevel ? 1 : 2; };
-        auto item_class = [&](const CqtItem &it) { return (!p.slide_off && is_slide_item(it)) ? 3 : level_class(it.level); };
-        for (int cls = 0; cls < (overlap ? 3 : 1) && !rc; ++cls) {
-            if (cls == 1) AMT_CUDA(cudaStreamWaitEvent(st, ev_mid, 0));
-            if (cls == 2) AMT_CUDA(cudaStreamWaitEvent(st, ev_all, 0));
-            // items are sorted by n_fft, then level: a launch takes a run of equal n_fft and equal class
+            return tiles * TT;
+        };
+        // Sliding-DFT launches of one class (3: shared ladder, 5: exact-ladder tails) on the side stream, one launch per CTA-size
+        // class (narrow bands first: they hold the longest tiles), so that a narrow band does not carry the idle warps, registers
+        // and shared memory of the widest one.  CTAs are handed out in grid order (z slowest): the items with the longest tiles
+        // (smallest hop: most frames and the longest lead-in per tile) go first so that they do not form the tail of the launch.
+        auto launch_slides = [&](int cls) -> int {
+            std::map<int, std::vector<int>> classes;
+            for (size_t i = 0; i < p.items.size(); ++i)
+                if (item_class(p, p.items[i], overlap) == cls) classes[slide_class(p.items[i])].push_back((int)i);
+            for (auto &kv : classes) {
+                std::vector<int> &idx = kv.second;
+                std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return p.items[a].hop < p.items[b].hop; });
+                std::vector<int> frames;
+                for (int i : idx) frames.push_back(cls == 5 ? tail_frames(p.items[i], slide_tile_frames(p.items[i].hop)) : maxTall);
+                const int r = launch_slide(p, cp, idx, frames, batch, cls == 5, lst);
+                if (r) return r;
+            }
+            return AMTFEAT_OK;
+        };
+        // FFT-per-frame launches of one class: items are sorted by (ladder, n_fft, level); a launch takes a run of equal n_fft
+        auto launch_ffts = [&](int cls, cudaStream_t s) -> int {
             size_t i0 = 0;
             while (i0 < p.items.size()) {
                 size_t i1 = i0;
-                while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft &&
-                       item_class(p.items[i1]) == item_class(p.items[i0]))
+                const int c0 = item_class(p, p.items[i0], overlap);
+                int frames = 0;
+                while (i1 < p.items.size() && p.items[i1].nfft == p.items[i0].nfft && p.items[i1].alt == p.items[i0].alt &&
+                       item_class(p, p.items[i1], overlap) == c0) {
+                    frames = std::max(frames, cls == 4 ? tail_frames(p.items[i1], 16384 / p.items[i1].nfft) : maxTall);
                     ++i1;
-                if (item_class(p.items[i0]) == cls) {
-                    const int NC = p.items[i0].nfft / 2, cnt = (int)(i1 - i0);
-                    switch (NC) {
-                        case 1024: rc = launch_cqt<1024>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 512: rc = launch_cqt<512>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 256: rc = launch_cqt<256>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 128: rc = launch_cqt<128>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 64: rc = launch_cqt<64>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 32: rc = launch_cqt<32>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 16: rc = launch_cqt<16>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        case 8: rc = launch_cqt<8>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                        default: rc = launch_cqt<4>(p, cp, (int)i0, cnt, batch, maxT, st); break;
-                    }
-                    if (rc) break;
+                }
+                if (c0 == cls && frames > 0) {
+                    const int r = launch_cqt_nc(p, cp, p.items[i0].nfft / 2, (int)i0, (int)(i1 - i0), batch, frames, cls == 4, s);
+                    if (r) return r;
                 }
                 i0 = i1;
             }
-            if (rc) break;
+            return AMTFEAT_OK;
+        };
+        if ((rc = launch_slides(3))) return rc;
+        // exact ladders: the tail of every level (level eds in one 2^eds : 1 pass over the audio), then their items
+        for (size_t a = 0; a < p.alts.size(); ++a) {
+            const AltLadder &al = p.alts[a];
+            for (int l = al.eds; l < al.eds + p.n_oct; ++l) {
+                TailParams tp{};
+                tp.audio = d_audio; tp.ladder = d_ladder; tp.meta = d_meta; tp.alt = (int)a; tp.level_out = l;
+                if (l == al.eds) { tp.taps = al.d_taps; tp.ntaps = (int)al.taps.size(); tp.factor = 1 << al.eds; tp.level_in = 0; }
+                else { tp.taps = p.d_taps64; tp.ntaps = (int)p.taps64.size(); tp.factor = 2; tp.level_in = l - 1; }
+                for (int head = 0; head < 2; ++head) {
+                    int count = 0;
+                    for (int b = 0; b < batch; ++b) {
+                        if (head) { if (metas[b].alt_first[a][l] != 0) count = std::max(count, metas[b].alt_hlen[a][l]); }
+                        else if (metas[b].alt_first[a][l] >= 0) count = std::max(count, metas[b].lvl_len[l] - metas[b].alt_first[a][l]);
+                    }
+                    if (count <= 0) continue;
+                    tp.head = head;
+                    dim3 grid((count + kThreads - 1) / kThreads, batch);
+                    ProfScope ps(p, "tail_decimate_kernel", lst);
+                    tail_decimate_kernel<<<grid, kThreads, 0, lst>>>(tp);
+                    AMT_CUDA(cudaGetLastError());
+                }
+            }
         }
-        if (overlap) {
-            // the caller's stream gets a dependency on everything the side stream was given (ladder and sliding-DFT items)
-            cudaStreamWaitEvent(st, ev_side, 0);
-            cudaEventDestroy(ev_fork);
-            cudaEventDestroy(ev_mid);
-            cudaEventDestroy(ev_all);
-            cudaEventDestroy(ev_side);
+        if (!p.alts.empty()) {
+            if ((rc = launch_ffts(4, lst))) return rc;
+            if ((rc = launch_slides(5))) return rc;
         }
-        if (rc) return rc;
+        for (int cls = 0; cls < (overlap ? 3 : 1); ++cls) {
+            if (cls == 1) AMT_CUDA(cudaStreamWaitEvent(st, ev_mid, 0));
+            if (cls == 2) AMT_CUDA(cudaStreamWaitEvent(st, ev_all, 0));
+            if ((rc = launch_ffts(cls, st))) return rc;
+        }
+        // `join` (destructor) gives the caller's stream a dependency on everything the side stream was given
     }
     if (c.decibels) {
         int64_t maxcount = (int64_t)p.F * maxT;

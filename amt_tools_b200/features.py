@@ -37,8 +37,9 @@ class _Plan(object):
         self.device_index = device_index
 
     def __del__(self):
-        if getattr(self, 'handle', None) is not None and self.handle.value:
-            _lib.lib.amtfeat_plan_destroy(self.handle)
+        lib = getattr(_lib, 'lib', None)        # None while the interpreter is shutting down
+        if lib is not None and getattr(self, 'handle', None) is not None and self.handle.value:
+            lib.amtfeat_plan_destroy(self.handle)
             self.handle = C.c_void_p()
 
 
@@ -91,6 +92,12 @@ class FeatureModule(object):
     def describe(self):
         buf = C.create_string_buffer(1 << 18)
         _lib.check(_lib.lib.amtfeat_plan_describe(self._host_plan.handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
+    def describe_clip(self, num_samples):
+        """How one clip of `num_samples` is laid out (frames, ladder levels, exact-ladder tails): tests / docs."""
+        buf = C.create_string_buffer(1 << 16)
+        _lib.check(_lib.lib.amtfeat_clip_describe(self._host_plan.handle, int(num_samples), buf, len(buf)))
         return json.loads(buf.value.decode())
 
     # ---- reference API ---------------------------------------------------------------------

@@ -110,6 +110,11 @@ AMTFEAT_API int amtfeat_out_shape(const amtfeat_plan *plan, int64_t num_samples,
 /* JSON description of the plan (ladder levels, n_fft per level, nnz, taps, ...) for tests / docs. */
 AMTFEAT_API int amtfeat_plan_describe(const amtfeat_plan *plan, char *buf, size_t capacity);
 
+/* JSON description of how ONE clip of num_samples is laid out (tests / docs): frames stored and computed, the frames each
+ * harmonic's dB maximum runs over (hvqt.py:123-128), the ladder level lengths and -- for harmonics librosa early-downsamples
+ * by 2^eds >= 4 in one resample call (vqt.py:183) -- the geometry of the exact ladders' tails. */
+AMTFEAT_API int amtfeat_clip_describe(const amtfeat_plan *plan, int64_t num_samples, char *buf, size_t capacity);
+
 /* Device workspace needed by amtfeat_process for a batch with these clip lengths. */
 AMTFEAT_API size_t amtfeat_workspace_bytes(const amtfeat_plan *plan, int batch, const int64_t *num_samples);
 

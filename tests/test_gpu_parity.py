@@ -1,14 +1,16 @@
 """
-Parity of the CUDA path (through the C-ABI) against the float64 oracle and the committed golden fixtures.
+Parity of the CUDA path (through the C-ABI) against the oracle and the committed golden fixtures.
 Run on the B200 box:  python -m pytest tests -m gpu
 
 Tolerances (BASELINE.json north_star; measured context in DESIGN.md "Parity"):
-  * linear magnitudes / powers: relative L2 <= 1e-5                                         (asserted)
-  * dB features, bins within 60 dB of the clip maximum: max-abs <= DB_TOL_TOP dB           (asserted)
-  * dB features, all bins down to the -80 dB floor: max-abs <= DB_TOL_ALL dB               (asserted)
-The 1e-3 dB bar of the north_star is met where float32 arithmetic allows it (STFT / MelSpec above -60 dB);
-the reference itself computes in float32 and deviates from the float64 truth by 2e-3 .. 2e-2 dB in the
-bottom 20 dB (measured with the float32 oracle), which is why DB_TOL_ALL is looser.
+  * linear magnitudes / powers: relative L2 <= 1e-5 against the float64 oracle                              (asserted)
+  * dB features, bins within 60 dB of the (clip, channel) maximum: max-abs <= 1e-3 dB against the float64 oracle,
+    EVERY module, whole clip (first and last frames included)                                                (asserted)
+  * dB features, all bins down to the -80 dB floor: max-abs <= DB_TOL_ALL dB                                 (asserted)
+  * the same against the float32 oracle (the precision the reference itself runs at: float32 audio -> complex64
+    spectra): the float32 oracle sits 1e-3 .. 3e-3 dB from the float64 one on bins 60 dB down, so two float32
+    computations cannot agree to 1e-3 dB there; asserted instead: the CUDA path is closer to the float64 truth than
+    the float32 oracle is, and within DB_TOL_F32 of the float32 oracle.
 """
 import os
 
@@ -23,14 +25,9 @@ from oracle import modules as om
 pytestmark = pytest.mark.gpu
 
 REL_L2_TOL = 1e-5
-DB_TOL_TOP = {'STFT': 1e-3, 'MelSpec': 1e-3, 'SignalPower': 1e-3, 'CQT': 5e-3, 'VQT': 5e-3, 'HCQT': 5e-3, 'HVQT': 5e-3}
-DB_TOL_ALL = {'STFT': 2e-2, 'MelSpec': 1e-2, 'SignalPower': 1e-3, 'CQT': 5e-2, 'VQT': 5e-2, 'HCQT': 5e-2, 'HVQT': 5e-2}
-# Harmonics that librosa early-downsamples by 4 or more in ONE resample call (eds >= 2, e.g. h = 0.5 of the HCQT) are
-# served from the shared cascaded 2:1 ladder (DESIGN.md "Known deviations" #1): identical in the pass band, but the
-# intermediate signal is truncated like librosa's own octave-to-octave steps, so the last ~1.5 s of those channels see a
-# slightly different end-of-signal transient.  They are checked with DB_TOL_TAIL there.
-DB_TOL_TAIL = 0.5
-TAIL_SECONDS = 1.5
+DB_TOL_TOP = 1e-3           # every module: the north_star bar, on bins within 60 dB of the maximum
+DB_TOL_ALL = 1e-2           # down to the -80 dB floor (a bin 80 dB down moves by 1e-2 dB when the peak's 1e-7 is added to it)
+DB_TOL_F32 = 5e-3           # against the float32 oracle, bins within 60 dB of the maximum
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden', 'golden_v1.npz')
 
 
@@ -40,6 +37,7 @@ def rel_l2(a, b):
 
 
 def db_errors(name, got, want):
+    """(max-abs over all bins, max-abs over the bins within 60 dB of the maximum), in dB."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     scale, thr = (1.0, -60.0) if name == 'SignalPower' else (80.0, 0.25)
     d = np.abs(got - want) * scale
@@ -97,19 +95,22 @@ def test_decibel_parity(idx):
     got = m.process_audio(y).cpu().numpy()
     want = o.process_audio(y)
     assert got.shape == want.shape
-    if name in ('HCQT', 'HVQT') and max(m.describe()['eds_ref']) >= 2:
-        tail = int(np.ceil(TAIL_SECONDS * sr / kw['hop_length']))
-        e_tail, _ = db_errors(name, got[..., -tail:], want[..., -tail:])
-        assert e_tail <= DB_TOL_TAIL, (name, 'tail', e_tail)
-        e_all, e_top = db_errors(name, got[..., :-tail], want[..., :-tail])
-    else:
-        e_all, e_top = db_errors(name, got, want)
-    assert e_top <= DB_TOL_TOP[name], (name, e_top)
-    assert e_all <= DB_TOL_ALL[name], (name, e_all)
+    e_all, e_top = db_errors(name, got, want)
+    assert e_top <= DB_TOL_TOP, (name, e_top)
+    assert e_all <= DB_TOL_ALL, (name, e_all)
     if name != 'SignalPower':
         assert got.min() >= 0.0 and got.max() == 1.0       # [0, 1] scaling, maximum exactly 1 (common.py:224-225)
     else:
         assert got.max() == 0.0 and got.min() >= -80.0
+    # the precision the reference runs at: float32 audio -> complex64 spectra
+    kw32 = dict(kw, decibels=True, dtype=np.float32)
+    if 'harmonics' in kw32:
+        kw32['harmonics'] = list(kw32['harmonics'])
+    want32 = np.asarray(getattr(om, 'O' + name)(**kw32).process_audio(y), np.float64)
+    _, f_top = db_errors(name, got, want32)
+    _, o_top = db_errors(name, want32, want)
+    assert f_top <= DB_TOL_F32, (name, f_top)
+    assert e_top <= max(o_top, 2e-4), (name, 'CUDA path further from the float64 oracle than the float32 oracle is', e_top, o_top)
 
 
 def test_golden_fixtures():
@@ -126,13 +127,12 @@ def test_golden_fixtures():
         assert got.shape == want.shape, case
         if kw.get('decibels', True):
             e_all, e_top = db_errors(name, got, want)
-            assert e_top <= DB_TOL_TOP[name] and e_all <= DB_TOL_ALL[name], (case, e_all, e_top)
-        elif case == 'hcqt_lin':
-            # channel 0 (h = 0.5, early-downsampled by 4) on a 1 s clip is all "tail": see DB_TOL_TAIL above
-            assert rel_l2(got[1:], want[1:]) <= REL_L2_TOL, case
-            assert rel_l2(got[0], want[0]) <= 5e-4, case
+            assert e_top <= DB_TOL_TOP and e_all <= DB_TOL_ALL, (case, e_all, e_top)
         else:
             assert rel_l2(got, want) <= REL_L2_TOL, case
+            if got.ndim == 3 and got.shape[0] > 1:      # every harmonic on its own, the early-downsampled ones included
+                for c in range(got.shape[0]):
+                    assert rel_l2(got[c], want[c]) <= REL_L2_TOL, (case, c)
 
 
 def test_analytic_known_answers_on_gpu():
@@ -220,6 +220,71 @@ def test_numpy_output_mode_and_combo():
     assert tuple(stack.shape) == (2, 84, 87)
 
 
+def _check_full(name, kw, y):
+    """dB and linear features of one full-size clip against the float64 oracle, channel by channel."""
+    m, o = make(name, kw, True)
+    got, want = m.process_audio(y).cpu().numpy(), o.process_audio(y)
+    assert got.shape == want.shape and got.shape[-1] == m.get_expected_frames(y)
+    for c in range(got.shape[0]):
+        e_all, e_top = db_errors(name, got[c], want[c])
+        assert e_top <= DB_TOL_TOP and e_all <= DB_TOL_ALL, (name, c, e_all, e_top)
+        # first and last two seconds on their own (zero-padded frames, end-of-signal transients of the decimators)
+        k = int(2.0 * kw['sample_rate'] / kw['hop_length'])
+        for sl in (slice(0, k), slice(-k, None)):
+            e_all, e_top = db_errors(name, got[c][:, sl], want[c][:, sl])
+            assert e_top <= DB_TOL_TOP and e_all <= DB_TOL_ALL, (name, c, sl, e_all, e_top)
+    m, o = make(name, kw, False)
+    got, want = m.process_audio(y).cpu().numpy(), o.process_audio(y)
+    for c in range(got.shape[0]):
+        assert rel_l2(got[c], want[c]) <= REL_L2_TOL, (name, c)
+        assert rel_l2(got[c][:, -64:], want[c][:, -64:]) <= REL_L2_TOL and rel_l2(got[c][:, :64], want[c][:, :64]) <= REL_L2_TOL, (name, c)
+
+
+def test_baseline_config1_cqt192_30s_against_oracle():
+    # BASELINE.json configs[0]: CQT(22050, hop 512, 192 bins, 24 bins / octave) on one 30 s clip, full size
+    _check_full('CQT', dict(sample_rate=22050, hop_length=512, n_bins=192, bins_per_octave=24), piano_like(22050 * 30, 22050, seed=0))
+
+
+def test_baseline_config3_hcqt_30s_against_oracle():
+    # BASELINE.json configs[2]: HCQT, 6 harmonics x 360 bins @ 60 bins / octave, hop 256, 30 s, full size
+    _check_full('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), piano_like(22050 * 30, 22050, seed=2000))
+
+
+def test_full_track_hcqt_240s_against_oracle():
+    # one 4-minute track of BASELINE.json configs[4] (the shape the headline metric is quoted on), every frame
+    _check_full('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), piano_like(22050 * 240, 22050, seed=4000))
+
+
+def test_abrupt_start_and_end_of_early_downsampled_harmonics():
+    # A clip cut out of the middle of a recording (TranscriptionDataset's random crops, datasets/common.py:116) starts and ends
+    # at full level: the harmonics librosa early-downsamples in one call (h = 0.5) see the decimator's ringing on both sides.
+    y = piano_like(22050 * 8, 22050, seed=77)[22050 * 2:22050 * 6 + 1234].copy()
+    y += (0.5 * np.sin(2 * np.pi * 55.0 * np.arange(len(y)) / 22050 + 0.3)).astype(np.float32)
+    _check_full('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60), y)
+    _check_full('HCQT', dict(sample_rate=22050, hop_length=512, harmonics=[0.25, 0.5, 1], n_bins=96, bins_per_octave=24), y)
+
+
+def test_exact_early_downsampling_switch(monkeypatch):
+    # AMTFEAT_EXACT_EDS=0 serves every harmonic from the shared ladder alone (round-1 behaviour): faster by a hair, and off
+    # at both ends of the clip on the channels librosa early-downsamples by >= 4.  The default must differ from it there.
+    y = piano_like(22050 * 4, 22050, seed=78)
+    y += (0.5 * np.sin(2 * np.pi * 55.0 * np.arange(len(y)) / 22050 + 0.3)).astype(np.float32)
+    kw = dict(sample_rate=22050, hop_length=256, decibels=False, n_bins=360, bins_per_octave=60)
+    exact = ab.HCQT(**kw)
+    assert exact.describe()['alt_mask'] == 1 and exact._dev_plan is not None
+    monkeypatch.setenv('AMTFEAT_EXACT_EDS', '0')
+    plain = ab.HCQT(**kw)
+    assert plain.describe()['alt_mask'] == 0 and plain._dev_plan is not None
+    monkeypatch.delenv('AMTFEAT_EXACT_EDS')
+    a, b = exact.process_audio(y).cpu().numpy(), plain.process_audio(y).cpu().numpy()
+    want = om.OHCQT(**kw).process_audio(y)
+    assert np.array_equal(a[1:], b[1:])                       # the other harmonics are untouched
+    mid = slice(400, a.shape[-1] - 400)
+    assert np.array_equal(a[0][:, mid], b[0][:, mid])         # interior frames of h = 0.5 come from the shared ladder either way
+    err_exact, err_plain = np.abs(a[0] - want[0]).max(), np.abs(b[0] - want[0]).max()
+    assert err_plain > 5 * err_exact, (err_exact, err_plain)
+
+
 def test_full_size_properties():
     # BASELINE-sized inputs, checked through size-independent properties instead of the (slow) oracle
     y = piano_like(22050 * 240, 22050, seed=60)
@@ -260,8 +325,10 @@ def test_fast_convolution_decimator_matches_direct_form(monkeypatch):
     # AMTFEAT_DECIM=direct).  Same taps, same ladder: the deepest levels must agree to float32 rounding.
     y = piano_like(22050 * 7 + 123, 22050, seed=81)
     kw = dict(sample_rate=22050, hop_length=256, decibels=False, n_bins=360, bins_per_octave=60)
+    monkeypatch.setenv('AMTFEAT_DECIM', 'fft32')
     fast = ab.HCQT(**kw)
-    assert fast.describe()['decimator'] == 'fft'
+    assert fast.describe()['decimator'] == 'fft32'
+    assert fast._dev_plan is not None            # the switch is read when the (lazily created) device plan is built
     a = fast.process_audio([y, y[:30011]])
     monkeypatch.setenv('AMTFEAT_DECIM', 'direct')
     direct = ab.HCQT(**kw)
@@ -312,11 +379,11 @@ def test_sliding_dft_matches_fft_per_frame(monkeypatch):
                 u, v = u.cpu().numpy(), v.cpu().numpy()
                 if db:
                     top = v > 0.25                                   # within 60 dB of the (clip, channel) maximum
-                    assert np.abs(u - v).max() * 80.0 < DB_TOL_ALL['HCQT']       # down to the -80 dB floor: 1e-6 of the peak is 1e-2 of a bin there
-                    assert (np.abs(u - v)[top].max() if top.any() else 0.0) * 80.0 < DB_TOL_TOP['HCQT']   # 3e-7 of the peak at -60 dB
+                    assert np.abs(u - v).max() * 80.0 < 5e-2                     # down to the -80 dB floor: 1e-6 of the peak is 1e-2 of a bin there
+                    assert (np.abs(u - v)[top].max() if top.any() else 0.0) * 80.0 < 2e-3   # two float32 algorithms, each within 1e-3 dB of the truth
                 else:
                     assert rel_l2(u, v) < 2e-6
                     assert np.abs(u - v).max() <= 3e-6 * np.abs(v).max()
     # the HCQT has sliding items: make sure the comparison above was not vacuous
     monkeypatch.delenv('AMTFEAT_SLIDE', raising=False)
-    assert sum(it['slide'] for it in ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()['items']) == 6
+    assert sum(it['slide'] for it in ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()['items'] if not it['alt']) == 6

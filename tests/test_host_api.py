@@ -93,9 +93,12 @@ def test_plan_description_matches_oracle_octave_plan():
     assert d['n_levels'] == 8 and d['n_octaves'] == 6 and d['channels'] == 6 and d['feature_size'] == 360
     by_fft = {}
     for it in d['items']:
-        by_fft.setdefault(it['n_fft'], []).append(it['level'])
+        if not it['alt']:
+            by_fft.setdefault(it['n_fft'], []).append(it['level'])
     assert sorted(by_fft) == [512, 1024] and by_fft[1024] == list(range(8)) and by_fft[512] == list(range(6))
-    assert sum(it['rows'] for it in d['items']) == 6 * 360
+    assert sum(it['rows'] for it in d['items'] if not it['alt']) == 6 * 360
+    # h = 0.5 (eds 2) has a second copy of its six octaves on the exact ladder (first / last frames only)
+    assert sorted((it['n_fft'], it['level'], it['rows']) for it in d['items'] if it['alt']) == [(1024, l, 60) for l in range(2, 8)]
     # the sparsified basis keeps the same number of entries as the oracle's (librosa) CSR bases, row for row
     from oracle import librosa_stages as ls
     d1 = ab.CQT(22050, 512, n_bins=192, bins_per_octave=24).describe()
@@ -119,7 +122,7 @@ def test_sliding_dft_items_are_the_deep_levels(monkeypatch):
     for it in d['items']:
         want = it['hop'] <= 16 and it['n_fft'] >= 128 and it['n_fft'] // it['hop'] >= 16
         assert it['slide'] == int(want), it
-    assert sorted((it['n_fft'], it['level']) for it in d['items'] if it['slide']) == \
+    assert sorted((it['n_fft'], it['level']) for it in d['items'] if it['slide'] and not it['alt']) == \
         [(512, 4), (512, 5), (1024, 4), (1024, 5), (1024, 6), (1024, 7)]
     d1 = ab.CQT(22050, 512, n_bins=192, bins_per_octave=24).describe()
     assert [it['level'] for it in d1['items'] if it['slide']] == [5, 6, 7]          # hop 16, 8, 4 against n_fft 256
