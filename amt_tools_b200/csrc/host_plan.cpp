@@ -530,13 +530,25 @@ static int build_vqt(Plan &p) {
                 p.decim_h64[2 * k] = v.real();
                 p.decim_h64[2 * k + 1] = v.imag();
             }
-            p.decim_tw64.resize(2 * 1024);
-            for (int m = 0; m < 1024; ++m) {
-                // exact octant symmetries keep cos / sin accurate to the last bit where it matters (m = 0, 512)
-                const double ang = -2.0 * kPi * (double)m / 2048.0;
-                p.decim_tw64[2 * m] = m == 512 ? 0.0 : std::cos(ang);
-                p.decim_tw64[2 * m + 1] = m == 0 ? 0.0 : std::sin(ang);
-            }
+            // per-pass twiddle tables of its Stockham transforms (kernels.cu stockham_pass): radix-4 passes with
+            // sub-transform size Ns = 4, 16, 64, 256: [r - 1][k] = exp(-2 pi i r k / (4 Ns)); then the radix-2 pass, Ns = 1024
+            p.decim_tw64.clear();
+            auto push_tw = [&](long long num, long long den) {   // exp(-2 pi i num / den), exact at the octant points
+                num %= den;
+                const double ang = -2.0 * kPi * (double)num / (double)den;
+                double c = std::cos(ang), sn = std::sin(ang);
+                if ((4 * num) % den == 0) {
+                    const int q = (int)(4 * num / den);
+                    c = q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
+                    sn = q == 1 ? -1.0 : q == 3 ? 1.0 : 0.0;
+                }
+                p.decim_tw64.push_back(c);
+                p.decim_tw64.push_back(sn);
+            };
+            for (int Ns = 4; Ns <= 256; Ns *= 4)
+                for (int r = 1; r < 4; ++r)
+                    for (int k = 0; k < Ns; ++k) push_tw((long long)r * k, 4ll * Ns);
+            for (int k = 0; k < 1024; ++k) push_tw(k, 2048);
         }
     }
 

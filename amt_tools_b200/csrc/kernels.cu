@@ -37,8 +37,8 @@
 #define AMT_MID_LEVEL 3        // projection launches are cut by ladder depth: level 0 | 1 .. AMT_MID_LEVEL | deeper
 #endif
 #ifndef AMT_SLIDE_RESEED
-#define AMT_SLIDE_RESEED 8     // most frames between exact re-seeds of the sliding-DFT phase P (recurrence P *= W^(k hop) in between);
-#endif                         // the interval shrinks with the hop: 16 / hop frames (hop 16: every frame, hop 8: every other one)
+#define AMT_SLIDE_RESEED 8     // hop <= 4: frames between exact re-seeds of the float32 sliding-DFT phase P (recurrence P *= W^(k hop) in between)
+#endif                         // (hop 8 / 16: the recurrence runs in float64 instead, see slide_run)
 #ifndef AMT_SLIDE_SPLIT
 #define AMT_SLIDE_SPLIT 1      // 0: one launch for all sliding items; 1: bands of at most 128 bins | wider; 2: one launch per CTA size
 #endif
@@ -681,12 +681,13 @@ __global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFf
 // ------------------------------------------------------------------------------------------------
 
 constexpr int kD64Threads = 256;
+constexpr int kD64Buf = 2048 + 2048 / 8;   // one padded buffer (double2)
 
 struct Dec64Params {
     const float *audio;
     float *ladder;
     const ClipMeta *meta;
-    const double2 *tw;   // exp(-2 pi i m / 2048), m < 1024
+    const double2 *tw;   // per-pass twiddle tables (host_plan.cpp decim_tw64): radix 4, Ns = 4, 16, 64, 256: [r - 1][k]; radix 2, Ns = 1024: [k]
     const double2 *H;    // response of the taps, k < 2048, times 1 / 2048
     int level_out, D, M, pairs_per_cta;
 };
@@ -696,45 +697,44 @@ __device__ __forceinline__ double2 dmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 dadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 dsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-// exp(-2 pi i m / 2048), 0 <= m < 2048, from the half table
-__device__ __forceinline__ double2 tw2048(const double2 *tw, int m) {
-    const double2 w = tw[m & 1023];
-    return (m & 1024) ? make_double2(-w.x, -w.y) : w;
-}
+// One extra 16-byte slot per 8: the stride-4 stores of the first radix-4 pass (and the stride-2 ones of the last pass) spread over
+// all eight 16-byte bank groups instead of two.
+__device__ __forceinline__ int ph64(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int tw64_off(int Ns) { return Ns == 4 ? 0 : Ns == 16 ? 12 : Ns == 64 ? 60 : Ns == 256 ? 252 : 1020; }
 
 // One Stockham pass of an N-point forward DFT (radix R, sub-transform size Ns so far): thread j takes inputs j + r N / R,
 // twiddles them by exp(-2 pi i r (j mod Ns) / (Ns R)), and writes the R-point DFT to (j / Ns) Ns R + (j mod Ns) + r Ns.
-template <int N, int R>
-__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw,
-                                              int Ns, int tid) {
-    const int stride = 2048 / (Ns * R);
+template <int N, int R, int Ns>
+__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw, int tid) {
+    const double2 *twp = tw + tw64_off(Ns);
+#pragma unroll
     for (int j = tid; j < N / R; j += kD64Threads) {
         const int k = j & (Ns - 1);
         double2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[j + r * (N / R)];
+        for (int r = 0; r < R; ++r) v[r] = in[ph64(j + r * (N / R))];
         if (Ns > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = dmul(v[r], tw2048(tw, r * k * stride));
+            for (int r = 1; r < R; ++r) v[r] = dmul(v[r], __ldg(twp + (r - 1) * Ns + k));
         }
         const int j0 = (j - k) * R + k;
         if (R == 4) {
             const double2 a = dadd(v[0], v[2]), b = dsub(v[0], v[2]), c = dadd(v[1], v[3]), d = dsub(v[1], v[3]);
             const double2 dmi = make_double2(d.y, -d.x);   // -i d
-            out[j0] = dadd(a, c);
-            out[j0 + Ns] = dadd(b, dmi);
-            out[j0 + 2 * Ns] = dsub(a, c);
-            out[j0 + 3 * Ns] = dsub(b, dmi);
+            out[ph64(j0)] = dadd(a, c);
+            out[ph64(j0 + Ns)] = dadd(b, dmi);
+            out[ph64(j0 + 2 * Ns)] = dsub(a, c);
+            out[ph64(j0 + 3 * Ns)] = dsub(b, dmi);
         } else {
-            out[j0] = dadd(v[0], v[1]);
-            out[j0 + Ns] = dsub(v[0], v[1]);
+            out[ph64(j0)] = dadd(v[0], v[1]);
+            out[ph64(j0 + Ns)] = dsub(v[0], v[1]);
         }
     }
 }
 
-__global__ void __launch_bounds__(kD64Threads, 2) decimate_fft64_kernel(const Dec64Params p) {
+__global__ void __launch_bounds__(kD64Threads, 3) decimate_fft64_kernel(const Dec64Params p) {
     extern __shared__ __align__(16) double2 smem64[];
-    double2 *s_tw = smem64, *b0 = s_tw + 1024, *b1 = b0 + 2048;
+    double2 *b0 = smem64, *b1 = b0 + kD64Buf;
     const int tid = threadIdx.x;
     const ClipMeta *cm = p.meta + blockIdx.y;
     const int len_out = cm->lvl_len[p.level_out], len_in = cm->lvl_len[p.level_out - 1];
@@ -742,41 +742,50 @@ __global__ void __launch_bounds__(kD64Threads, 2) decimate_fft64_kernel(const De
     const int pair0 = blockIdx.x * p.pairs_per_cta;
     if (pair0 >= npairs) return;
     const int pair1 = min(npairs, pair0 + p.pairs_per_cta);
-    for (int i = tid; i < 1024; i += kD64Threads) s_tw[i] = p.tw[i];
     const float *src = (p.level_out == 1 ? p.audio : p.ladder) + cm->lvl_off[p.level_out - 1];
     float *dst = p.ladder + cm->lvl_off[p.level_out];
     for (int pair = pair0; pair < pair1; ++pair) {
         const long long mA = (long long)pair * 2 * p.M, mB = mA + p.M;
         const bool haveB = mB < len_out;
-        const long long baseA = 2 * mA - p.D, baseB = 2 * mB - p.D;
-        __syncthreads();   // the previous pair's result has been read (first time: nothing)
-        for (int n = tid; n < 2048; n += kD64Threads) {
-            const long long ia = baseA + n, ib = baseB + n;
-            const float xa = (ia >= 0 && ia < len_in) ? __ldg(src + ia) : 0.f;
-            const float xb = (haveB && ib >= 0 && ib < len_in) ? __ldg(src + ib) : 0.f;
-            b0[n] = make_double2((double)xa, (double)xb);
-        }
-        __syncthreads();   // (also covers the twiddle table the first time)
-        stockham_pass<2048, 4>(b0, b1, s_tw, 1, tid);    __syncthreads();
-        stockham_pass<2048, 4>(b1, b0, s_tw, 4, tid);    __syncthreads();
-        stockham_pass<2048, 4>(b0, b1, s_tw, 16, tid);   __syncthreads();
-        stockham_pass<2048, 4>(b1, b0, s_tw, 64, tid);   __syncthreads();
-        stockham_pass<2048, 4>(b0, b1, s_tw, 256, tid);  __syncthreads();
-        stockham_pass<2048, 2>(b1, b0, s_tw, 1024, tid); __syncthreads();
-        // spectral product, fold onto 1024 points, conjugate (the inverse transform is conj(DFT(conj .)))
-        for (int k = tid; k < 1024; k += kD64Threads) {
-            const double2 w0 = dmul(b0[k], __ldg(p.H + k)), w1 = dmul(b0[k + 1024], __ldg(p.H + k + 1024));
-            b1[k] = make_double2(w0.x + w1.x, -(w0.y + w1.y));
+        const long long baseA = 2 * mA - p.D, baseB = 2 * mB - p.D;      // even: D is even
+        const bool interior = baseA >= 0 && baseB + 2048 <= len_in;
+        if (pair != pair0) __syncthreads();   // the previous pair's result has been read
+        for (int n = 2 * tid; n < 2048; n += 2 * kD64Threads) {
+            float2 xa, xb;
+            if (interior) {
+                xa = __ldg(reinterpret_cast<const float2 *>(src + baseA + n));
+                xb = __ldg(reinterpret_cast<const float2 *>(src + baseB + n));
+            } else {
+                const long long ia = baseA + n, ib = baseB + n;
+                xa.x = (ia >= 0 && ia < len_in) ? __ldg(src + ia) : 0.f;
+                xa.y = (ia + 1 >= 0 && ia + 1 < len_in) ? __ldg(src + ia + 1) : 0.f;
+                xb.x = (haveB && ib >= 0 && ib < len_in) ? __ldg(src + ib) : 0.f;
+                xb.y = (haveB && ib + 1 >= 0 && ib + 1 < len_in) ? __ldg(src + ib + 1) : 0.f;
+            }
+            b0[ph64(n)] = make_double2((double)xa.x, (double)xb.x);
+            b0[ph64(n + 1)] = make_double2((double)xa.y, (double)xb.y);
         }
         __syncthreads();
-        stockham_pass<1024, 4>(b1, b0, s_tw, 1, tid);    __syncthreads();
-        stockham_pass<1024, 4>(b0, b1, s_tw, 4, tid);    __syncthreads();
-        stockham_pass<1024, 4>(b1, b0, s_tw, 16, tid);   __syncthreads();
-        stockham_pass<1024, 4>(b0, b1, s_tw, 64, tid);   __syncthreads();
-        stockham_pass<1024, 4>(b1, b0, s_tw, 256, tid);  __syncthreads();
+        stockham_pass<2048, 4, 1>(b0, b1, p.tw, tid);    __syncthreads();
+        stockham_pass<2048, 4, 4>(b1, b0, p.tw, tid);    __syncthreads();
+        stockham_pass<2048, 4, 16>(b0, b1, p.tw, tid);   __syncthreads();
+        stockham_pass<2048, 4, 64>(b1, b0, p.tw, tid);   __syncthreads();
+        stockham_pass<2048, 4, 256>(b0, b1, p.tw, tid);  __syncthreads();
+        stockham_pass<2048, 2, 1024>(b1, b0, p.tw, tid); __syncthreads();
+        // spectral product, fold onto 1024 points, conjugate (the inverse transform is conj(DFT(conj .)))
+        for (int k = tid; k < 1024; k += kD64Threads) {
+            const double2 w0 = dmul(b0[ph64(k)], __ldg(p.H + k)), w1 = dmul(b0[ph64(k + 1024)], __ldg(p.H + k + 1024));
+            b1[ph64(k)] = make_double2(w0.x + w1.x, -(w0.y + w1.y));
+        }
+        __syncthreads();
+        stockham_pass<1024, 4, 1>(b1, b0, p.tw, tid);    __syncthreads();
+        stockham_pass<1024, 4, 4>(b0, b1, p.tw, tid);    __syncthreads();
+        stockham_pass<1024, 4, 16>(b1, b0, p.tw, tid);   __syncthreads();
+        stockham_pass<1024, 4, 64>(b0, b1, p.tw, tid);   __syncthreads();
+        stockham_pass<1024, 4, 256>(b1, b0, p.tw, tid);  __syncthreads();
         // b0[j] = conj(ydA[j] + i ydB[j]); output m = m0 + j - D for j >= D
         for (int j = p.D + tid; j < 1024; j += kD64Threads) {
-            const double2 r = b0[j];
+            const double2 r = b0[ph64(j)];
             const long long ma = mA + j - p.D, mb = mB + j - p.D;
             if (ma < len_out) dst[ma] = (float)r.x;
             if (haveB && mb < len_out) dst[mb] = (float)(-r.y);
@@ -837,9 +846,17 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
     const long long c = (long long)p.factor * m + D;
     // i = c - k must lie in [lo, hi)
     const long long k_lo = max(0ll, c - hi + 1), k_hi = min((long long)p.ntaps - 1, c - lo);
-    double acc = 0.0;
-    for (long long k = k_lo; k <= k_hi; ++k) acc = fma(__ldg(p.taps + k), (double)src[c - k], acc);
-    dst[m] = (float)acc;
+    // four independent chains (a single one is bound by the latency of the float64 FMA, not by its throughput)
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long long k = k_lo;
+    for (; k + 3 <= k_hi; k += 4) {
+        a0 = fma(__ldg(p.taps + k), (double)src[c - k], a0);
+        a1 = fma(__ldg(p.taps + k + 1), (double)src[c - k - 1], a1);
+        a2 = fma(__ldg(p.taps + k + 2), (double)src[c - k - 2], a2);
+        a3 = fma(__ldg(p.taps + k + 3), (double)src[c - k - 3], a3);
+    }
+    for (; k <= k_hi; ++k) a0 = fma(__ldg(p.taps + k), (double)src[c - k], a0);
+    dst[m] = (float)((a0 + a1) + (a2 + a3));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -856,10 +873,13 @@ __device__ __forceinline__ void project_block2(const CqtBlock4 *bl, const float4
                                                int decibels, int *s_max, unsigned gmask, int glanes, bool leader, bool vec2,
                                                unsigned skip, const int *__restrict__ tmax) {
     const int ndst = bl->ndst;
-    unsigned live_d = 0;
-    for (int d = 0; d < ndst; ++d)
-        if (!((skip >> bl->chan[d]) & 1u)) live_d |= 1u << d;
-    if (!live_d) return;
+    unsigned live_d = (1u << ndst) - 1u;
+    if (skip) {     // only the first / last tiles of a clip, and only for plans with exact ladders
+        live_d = 0;
+        for (int d = 0; d < ndst; ++d)
+            if (!((skip >> bl->chan[d]) & 1u)) live_d |= 1u << d;
+        if (!live_d) return;
+    }
     const int steps = bl->steps;
     const float2 z2 = make_float2(0.f, 0.f);
     float2 rA01 = z2, nA01 = z2, iA01 = z2, jA01 = z2, rA23 = z2, nA23 = z2, iA23 = z2, jA23 = z2;
@@ -1248,9 +1268,11 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
                                           const ClipMeta *cm, int t0, int tend, int Tt, float *s_reg, int *s_max) {
     constexpr int FL = kSlideFL, DP = kSlideDP, HP = (H + 1) / 2;
     // An error of P scales the whole increment of a frame (hop samples of the FULL signal), so it matters most where the hop is
-    // large: measured on the HCQT, hop 16 / 8 with a re-seed every 8 frames were the least accurate items of the plan (9e-4 dB
-    // on bins 60 dB down); re-seeding from the exact table costs one cached load per frame against 4 hop flops.
-    constexpr int RESEED = (16 / H) < 1 ? 1 : (16 / H) > AMT_SLIDE_RESEED ? AMT_SLIDE_RESEED : (16 / H);
+    // large: measured on the HCQT, hop 16 / 8 with a float32 recurrence re-seeded every 8 frames were the least accurate items of
+    // the plan (9e-4 dB on bins 60 dB down).  There the recurrence runs in float64 on the otherwise idle FP64 pipe (4 operations
+    // + 2 conversions per frame against 4 hop float32 flops): exact to 1e-16 per step, never re-seeded, rounded once per frame.
+    constexpr bool PD = H >= 8;
+    constexpr int RESEED = AMT_SLIDE_RESEED;
     const int tid = threadIdx.x, NT = blockDim.x;
     const int N = it.nfft, NC = N >> 1, Q = N / H;
     const int kb = it.kmax - it.kmin + 1;
@@ -1276,6 +1298,12 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     const float2 R = tw_full(tw2, k * H, NC);
     float2 B = make_float2(0.f, 0.f), cmp = make_float2(0.f, 0.f), P = make_float2(1.f, 0.f);
     auto seed = [&](int t) { return tw_full(tw2, k * ((t * H) & (N - 1)), NC); };
+    double2 Pd = make_double2(1.0, 0.0), Rd = make_double2(1.0, 0.0);
+    if (PD) {
+        sincospi(-2.0 * (double)((k * H) & (N - 1)) / (double)N, &Rd.y, &Rd.x);
+        sincospi(-2.0 * (double)((k * (((t0 - Q) * H) & (N - 1))) & (N - 1)) / (double)N, &Pd.y, &Pd.x);
+        P = make_float2((float)Pd.x, (float)Pd.y);
+    }
     // B += P * sum_m xs[m] W^(k m);  P *= W^(k H)
     auto step = [&](const float *xs) {
         float2 are = make_float2(0.f, 0.f), aim = make_float2(0.f, 0.f);
@@ -1304,14 +1332,19 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
         cmp.y = (ny - B.y) - yy;
         B.x = nx;
         B.y = ny;
-        P = cmul(P, R);
+        if (PD) {
+            Pd = make_double2(fma(Pd.x, Rd.x, -Pd.y * Rd.y), fma(Pd.x, Rd.y, Pd.y * Rd.x));
+            P = make_float2((float)Pd.x, (float)Pd.y);
+        } else {
+            P = cmul(P, R);
+        }
     };
 
     // lead-in: the first window of the tile enters sample group by sample group
     if (active) {
 #pragma unroll 2
         for (int u = 0; u < Q; ++u) {
-            if ((u & (RESEED - 1)) == 0) P = seed(t0 - Q + u);
+            if (!PD && (u & (RESEED - 1)) == 0) P = seed(t0 - Q + u);
             step(s_x + u * H);
         }
     }
@@ -1334,7 +1367,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
             float2 *dp = Dbuf + tid * DP;
 #pragma unroll 4
             for (int f = 0; f < FL; ++f) {
-                if ((f & (RESEED - 1)) == 0) P = seed(t0 + c0 + f);
+                if (!PD && (f & (RESEED - 1)) == 0) P = seed(t0 + c0 + f);
                 dp[f] = make_float2(fmaf(P.x, B.x, P.y * B.y), fmaf(P.x, B.y, -P.y * B.x));   // conj(P) * B
                 step(s_x + (c0 + f) * H);
             }
@@ -2104,8 +2137,8 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 dp.tw = reinterpret_cast<const double2 *>(p.d_decim_tw64); dp.H = reinterpret_cast<const double2 *>(p.d_decim_h64);
                 dp.level_out = l; dp.D = D; dp.M = 1024 - D;
                 const int64_t npairs = (len + 2 * dp.M - 1) / (2 * dp.M);
-                dp.pairs_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs * batch / (148 * 2 * 2)));
-                const size_t fsmem = (size_t)(1024 + 2 * 2048) * sizeof(double2);
+                dp.pairs_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs * batch / (148 * 3 * 2)));
+                const size_t fsmem = (size_t)(2 * kD64Buf) * sizeof(double2);
                 dim3 grid((unsigned)((npairs + dp.pairs_per_cta - 1) / dp.pairs_per_cta), batch);
                 ProfScope ps(p, "decimate_fft64_kernel", lst);
                 decimate_fft64_kernel<<<grid, kD64Threads, fsmem, lst>>>(dp);
