@@ -806,9 +806,14 @@ struct TailParams {
     const ClipMeta *meta;
     const double *taps;
     int ntaps, factor, level_in, level_out, alt, head;   // head: the head piece [0, alt_hlen) instead of the tail piece [alt_first, len)
+    int taps_smem;                                       // the taps fit in shared memory next to the staged input
 };
 
+// A CTA produces kThreads consecutive outputs.  Polyphase form: tap k = F q + ph of output m reads x[F (m - q) + D - ph], so the
+// input span is staged in shared memory de-interleaved by phase, as float64: X[ph][j] = x[F (m0 + j - nq + 1) + D - ph].  The
+// inner loop is then one conflict-free 8-byte load, one broadcast tap load and one float64 FMA per tap (FP64-pipe bound).
 __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
+    extern __shared__ __align__(16) double tsm[];
     const ClipMeta *cm = p.meta + blockIdx.y;
     long long first, end;
     float *dst;
@@ -824,8 +829,8 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         end = cm->lvl_len[p.level_out];
         dst = p.ladder + cm->alt_off[p.alt][p.level_out];
     }
-    const long long m = first + (long long)blockIdx.x * kThreads + threadIdx.x;
-    if (m >= end) return;
+    const long long m0 = first + (long long)blockIdx.x * kThreads;
+    if (m0 >= end) return;
     const float *src;
     long long lo, hi;   // samples of the input piece that exist; everything outside reads as zero (true for < 0 and >= len; the
                         // geometry guarantees that nothing else is ever asked for, tests/test_exact_ladder.py)
@@ -842,21 +847,40 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         lo = cm->alt_first[p.alt][p.level_in];
         hi = cm->lvl_len[p.level_in];
     }
-    const int D = (p.ntaps - 1) / 2;
-    const long long c = (long long)p.factor * m + D;
-    // i = c - k must lie in [lo, hi)
-    const long long k_lo = max(0ll, c - hi + 1), k_hi = min((long long)p.ntaps - 1, c - lo);
-    // four independent chains (a single one is bound by the latency of the float64 FMA, not by its throughput)
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    long long k = k_lo;
-    for (; k + 3 <= k_hi; k += 4) {
-        a0 = fma(__ldg(p.taps + k), (double)src[c - k], a0);
-        a1 = fma(__ldg(p.taps + k + 1), (double)src[c - k - 1], a1);
-        a2 = fma(__ldg(p.taps + k + 2), (double)src[c - k - 2], a2);
-        a3 = fma(__ldg(p.taps + k + 3), (double)src[c - k - 3], a3);
+    const int F = p.factor, D = (p.ntaps - 1) / 2;
+    const int nq = (p.ntaps + F - 1) / F;          // taps per phase
+    const int J = kThreads + nq - 1, JP = J | 1;   // entries per phase (odd pitch)
+    double *X = tsm, *hs = tsm + (size_t)F * JP;   // hs[ph * nq + q] = taps[F q + ph]
+    if (p.taps_smem)
+        for (int i = threadIdx.x; i < F * nq; i += kThreads) {
+            const int ph = i / nq, q = i - ph * nq, k = F * q + ph;
+            hs[i] = k < p.ntaps ? __ldg(p.taps + k) : 0.0;
+        }
+    const long long g0 = (long long)F * (m0 - nq + 1) + D;     // X[ph][j] = x[g0 + F j - ph]
+    for (int i = threadIdx.x; i < F * J; i += kThreads) {
+        const int u = i - (F - 1);                                // u = F j - ph, -(F - 1) <= u <= F (J - 1)
+        const int ph = (F - 1) - ((u + F - 1) % F), j = (u + ph) / F;
+        const long long g = g0 + u;
+        X[ph * JP + j] = (g >= lo && g < hi) ? (double)src[g] : 0.0;
     }
-    for (; k <= k_hi; ++k) a0 = fma(__ldg(p.taps + k), (double)src[c - k], a0);
-    dst[m] = (float)((a0 + a1) + (a2 + a3));
+    __syncthreads();
+    const long long m = m0 + threadIdx.x;
+    if (m >= end) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int ph = 0; ph < F; ++ph) {
+        const double *xp = X + ph * JP + threadIdx.x + nq - 1, *hp = hs + ph * nq;
+        if (p.taps_smem) {
+            int q = 0;
+            for (; q + 1 < nq; q += 2) {
+                a0 = fma(hp[q], xp[-q], a0);
+                a1 = fma(hp[q + 1], xp[-q - 1], a1);
+            }
+            if (q < nq) a0 = fma(hp[q], xp[-q], a0);
+        } else {     // very long one-shot filters (2^eds >= 32): taps straight from global memory (warp-uniform loads)
+            for (int q = 0; F * q + ph < p.ntaps; ++q) a0 = fma(__ldg(p.taps + F * q + ph), xp[-q], a0);
+        }
+    }
+    dst[m] = (float)(a0 + a1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1638,6 +1662,7 @@ int upload_plan(Plan &p) {
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(cqt_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
@@ -2236,8 +2261,13 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                     if (count <= 0) continue;
                     tp.head = head;
                     dim3 grid((count + kThreads - 1) / kThreads, batch);
+                    const int nq = (tp.ntaps + tp.factor - 1) / tp.factor;
+                    const size_t xbytes = (size_t)tp.factor * ((kThreads + nq - 1) | 1) * sizeof(double), hbytes = (size_t)tp.factor * nq * sizeof(double);
+                    tp.taps_smem = xbytes + hbytes <= 200 * 1024;
+                    const size_t tsmem = xbytes + (tp.taps_smem ? hbytes : 0);
+                    if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
                     ProfScope ps(p, "tail_decimate_kernel", lst);
-                    tail_decimate_kernel<<<grid, kThreads, 0, lst>>>(tp);
+                    tail_decimate_kernel<<<grid, kThreads, tsmem, lst>>>(tp);
                     AMT_CUDA(cudaGetLastError());
                 }
             }

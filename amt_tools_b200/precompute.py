@@ -2,7 +2,8 @@
 Bulk feature precompute + cache writer -- the caller of the hot path named by BASELINE config 5
 (SURVEY.md 8f rank 1).  The reference computes one track at a time inside `TranscriptionDataset.__getitem__`
 and `np.savez_compressed`s synchronously (datasets/common.py:212-295); here a whole corpus shard is pushed
-through the GPU in ragged batches while a thread pool compresses and writes the previous batch.
+through the C-ABI pipelined executor (amtfeat_pipeline_*) in ragged batches over reused pinned host buffers while a
+thread pool compresses and writes the previous batch.
 
 The on-disk format is the reference's, so existing caches stay loadable and new ones are readable by the
 unmodified `calculate_feats` (datasets/common.py:242-250):
@@ -27,26 +28,117 @@ def feats_path(save_loc, dataset_name, data_proc, track):
 
 
 def _write(path, fs, hop_length, feats, compressed):
+    """One cache file in the reference's format.  Written next to its final name and renamed into place: the loader (like the
+    reference's, datasets/common.py:242) takes the existence of the file as a cache hit, so a killed run must not leave a
+    truncated one behind."""
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    (np.savez_compressed if compressed else np.savez)(path, **{KEY_FS: fs, KEY_HOP: hop_length, KEY_FEATS: feats})
+    tmp = '%s.tmp.%d' % (path, os.getpid())
+    try:
+        with open(tmp, 'wb') as f:
+            (np.savez_compressed if compressed else np.savez)(f, **{KEY_FS: fs, KEY_HOP: hop_length, KEY_FEATS: feats})
+        os.replace(tmp, path)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
     return path
 
 
 def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world_size=1, max_batch_seconds=960.0,
-                        overwrite=False, compressed=True, writers=4, keep_on_device=False):
+                        overwrite=False, compressed=True, writers=4, keep_on_device=False, ring=3, stats=None):
     """
     Compute and cache the features of every track this rank owns.
 
-    tracks : dict  track name -> 1-D float32 audio (np.ndarray or torch.Tensor), already at data_proc's sample rate
+    tracks : dict  track name -> 1-D float32 audio (np.ndarray or CPU torch.Tensor), already at data_proc's sample rate
     Returns {track: path} (and, with keep_on_device=True, {track: (path, CUDA tensor)} for device-resident consumers).
     Tracks whose cache file exists are skipped unless overwrite=True (datasets/common.py:242: cache hit -> load).
+
+    The batches run on the C-ABI pipelined executor (amtfeat_pipeline_*: upload / compute / download streams over `ring` device
+    staging slots) with `ring` reused pinned host buffers on either side; `writers` threads compress / write batch i - 1 while
+    batch i is on the GPU.  `stats` (dict) receives the seconds spent waiting for the GPU and for the writers.
     """
+    if not hasattr(data_proc, '_dev_plan') or not hasattr(data_proc, 'device'):
+        raise TypeError('precompute_features needs a single feature module of amt_tools_b200.features (one plan, one device); '
+                        'run the modules of a FeatureCombo one by one')
     names = sorted(tracks)
     lengths = [int(tracks[n].shape[-1]) for n in names]
     mine = shard.shard_tracks(lengths, world_size, rank)
     todo = [i for i in mine if overwrite or not os.path.exists(feats_path(save_loc, dataset_name, data_proc, names[i]))]
     budget = int(max_batch_seconds * data_proc.get_sample_rate())
     batches = shard.make_batches(todo, lengths, budget)
+    if keep_on_device:
+        return _precompute_resident(batches, tracks, names, data_proc, save_loc, dataset_name, compressed, writers)
+    if not batches:
+        return {}
+    import time
+    from .pipeline import Pipeline
+    fs, hop = data_proc.get_sample_rate(), data_proc.get_hop_length()
+    # layout of every batch: clip offsets inside the (4-element aligned) packed audio, output offsets, workspace
+    plans = []
+    for batch in batches:
+        lens = [lengths[i] for i in batch]
+        in_off, total_in = [], 0
+        for n in lens:
+            in_off.append(total_in)
+            total_in += (n + 3) // 4 * 4
+        shapes, sizes, out_off, _, _, ws_bytes, total_out = data_proc._batch_layout(lens)
+        plans.append((batch, lens, in_off, max(total_in, 4), shapes, sizes, out_off, max(total_out, 4), ws_bytes))
+    max_in, max_out = max(p[3] for p in plans), max(p[7] for p in plans)
+    ring = max(2, int(ring))
+    pipe = Pipeline(data_proc.device.index, ring, max_in, max_out, max(p[8] for p in plans))
+    h_in = [torch.empty(max_in, dtype=torch.float32).pin_memory() for _ in range(ring)]
+    h_out = [torch.empty(max_out, dtype=torch.float32).pin_memory() for _ in range(ring)]
+    busy = [[] for _ in range(ring)]          # writer futures still reading a host output slot
+    out, pending = {}, []
+    t_gpu = t_writers = 0.0
+
+    def flush(item, pool):
+        nonlocal t_gpu
+        slot, ticket, plan = item
+        t = time.perf_counter()
+        pipe.wait(ticket)
+        t_gpu += time.perf_counter() - t
+        batch, _, _, _, shapes, sizes, out_off, _, _ = plan
+        for j, i in enumerate(batch):
+            feats = h_out[slot][out_off[j]:out_off[j] + sizes[j]].view(shapes[j]).numpy()
+            fut = pool.submit(_write, feats_path(save_loc, dataset_name, data_proc, names[i]), fs, hop, feats, compressed)
+            busy[slot].append(fut)
+            out[names[i]] = fut
+
+    try:
+        with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
+            for b, plan in enumerate(plans):
+                slot = b % ring
+                while len(pending) >= ring - 1:                                  # keep ring - 1 batches in flight
+                    flush(pending.pop(0), pool)
+                t = time.perf_counter()
+                for fut in busy[slot]:                                           # the writers of batch b - ring are done with this slot
+                    fut.result()
+                t_writers += time.perf_counter() - t
+                busy[slot] = []
+                batch, lens, in_off, total_in, _, _, out_off, total_out, _ = plan
+                for i, o, n in zip(batch, in_off, lens):
+                    a = tracks[names[i]]
+                    a = a.detach().cpu() if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+                    h_in[slot][o:o + n].copy_(a.to(torch.float32))
+                ticket = pipe.submit(data_proc, h_in[slot], in_off, lens, out_off, h_out[slot], total_in, total_out)
+                pending.append((slot, ticket, plan))
+            while pending:
+                flush(pending.pop(0), pool)
+            t = time.perf_counter()
+            for k in list(out):
+                out[k] = out[k].result()
+            t_writers += time.perf_counter() - t
+    finally:
+        pipe.wait(-1)
+        pipe.close()
+    if stats is not None:
+        stats.update(wait_gpu_s=t_gpu, wait_writers_s=t_writers, batches=len(plans), tracks=len(out))
+    return out
+
+
+def _precompute_resident(batches, tracks, names, data_proc, save_loc, dataset_name, compressed, writers):
+    """keep_on_device=True: the features also stay on the GPU for a consumer there, so every batch gets its own device
+    tensors (torch allocations on the current stream) instead of the pipeline's reused staging slots."""
     fs, hop = data_proc.get_sample_rate(), data_proc.get_hop_length()
     out, pending = {}, []
     copy_stream = torch.cuda.Stream(data_proc.device)
@@ -65,16 +157,13 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
                     host.append(h)
                 copied = torch.cuda.Event()
                 copied.record(copy_stream)
-            pending.append((batch, feats if keep_on_device else None, host, copied))
+            pending.append((batch, feats, host, copied))
             while len(pending) > 1:                                                    # write batch i-1 while batch i computes
                 _flush(pending.pop(0), names, fs, hop, save_loc, dataset_name, data_proc, pool, compressed, out)
         while pending:
             _flush(pending.pop(0), names, fs, hop, save_loc, dataset_name, data_proc, pool, compressed, out)
         for k, v in list(out.items()):
-            if isinstance(v, tuple):
-                out[k] = (v[0].result(), v[1])
-            else:
-                out[k] = v.result()
+            out[k] = (v[0].result(), v[1])
     return out
 
 
@@ -84,7 +173,7 @@ def _flush(item, names, fs, hop, save_loc, dataset_name, data_proc, pool, compre
     for j, i in enumerate(batch):
         path = feats_path(save_loc, dataset_name, data_proc, names[i])
         fut = pool.submit(_write, path, fs, hop, host[j].numpy(), compressed)
-        out[names[i]] = (fut, dev[j]) if dev is not None else fut
+        out[names[i]] = (fut, dev[j])
 
 
 def load_features(path):
