@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libamtfeat.so')
 SOURCES = ['api.cpp', 'host_plan.cpp', 'kernels.cu', 'ingest.cu']
-HEADERS = ['plan.h', 'fft_device.cuh', os.path.join('..', '..', 'include', 'amtfeat.h')]
+HEADERS = ['plan.h', 'fft_device.cuh', 'device_guard.h', os.path.join('..', '..', 'include', 'amtfeat.h')]
 
 
 def _nvcc():

@@ -8,6 +8,7 @@
 #include <vector>
 #include <algorithm>
 
+#include "device_guard.h"
 #include "plan.h"
 
 struct amtfeat_plan {
@@ -206,7 +207,7 @@ extern "C" {
 
 void amtfeat_pipeline_destroy(amtfeat_pipeline *pipe) {
     if (!pipe) return;
-    cudaSetDevice(pipe->device);
+    amtfeat::DeviceGuard guard(pipe->device);
     if (pipe->s_d2h) cudaStreamSynchronize(pipe->s_d2h);
     for (auto &s : pipe->slots) {
         if (s.d_audio) cudaFree(s.d_audio);
@@ -223,7 +224,8 @@ void amtfeat_pipeline_destroy(amtfeat_pipeline *pipe) {
 }
 
 static int pipeline_init(amtfeat_pipeline *p) {
-    PIPE_CUDA(cudaSetDevice(p->device));
+    amtfeat::DeviceGuard guard(p->device);
+    PIPE_CUDA(guard.status);
     PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
     PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
     PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
@@ -261,7 +263,8 @@ int amtfeat_pipeline_submit(amtfeat_pipeline *pipe, const amtfeat_plan *plan, co
     if (audio_elems > pipe->max_audio || out_elems > pipe->max_out) { amtfeat::set_error("batch larger than the pipeline's staging buffers"); return AMTFEAT_ERR_INVALID; }
     const size_t ws = amtfeat::workspace_bytes(plan->p, batch, num_samples);
     if (ws > pipe->max_ws) { amtfeat::set_error("batch needs a larger workspace than the pipeline was created with"); return AMTFEAT_ERR_WORKSPACE; }
-    PIPE_CUDA(cudaSetDevice(pipe->device));
+    amtfeat::DeviceGuard guard(pipe->device);
+    PIPE_CUDA(guard.status);
     amtfeat_pipeline::Slot &s = pipe->slots[pipe->next_ticket % pipe->nslots];
     // upload: the kernels that last read this slot's audio must be done
     PIPE_CUDA(cudaStreamWaitEvent(pipe->s_h2d, s.computed, 0));
@@ -285,7 +288,8 @@ int amtfeat_pipeline_submit(amtfeat_pipeline *pipe, const amtfeat_plan *plan, co
 
 int amtfeat_pipeline_wait(amtfeat_pipeline *pipe, int64_t ticket) {
     if (!pipe) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
-    PIPE_CUDA(cudaSetDevice(pipe->device));
+    amtfeat::DeviceGuard guard(pipe->device);
+    PIPE_CUDA(guard.status);
     if (ticket < 0 || ticket + pipe->nslots < pipe->next_ticket) {   // everything (or a ticket whose slot was already recycled)
         PIPE_CUDA(cudaStreamSynchronize(pipe->s_d2h));
         return AMTFEAT_OK;

@@ -11,6 +11,8 @@
 // pinned by the reference's own formulas.
 #include <cuda_runtime.h>
 
+#include "device_guard.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -81,7 +83,9 @@ int resampler_build(Resampler &r, double sr_orig, double sr_new, int filter) {
     return AMTFEAT_OK;
 }
 
-int64_t resampler_out_len(const Resampler &r, int64_t n) { return (int64_t)((double)n * r.ratio); }   // int(n * ratio)
+// librosa.resample(..., fix=True): resampy allocates int(n * ratio) samples and librosa.util.fix_length pads the result with
+// zeros to ceil(n * ratio) -- one extra (zero) sample whenever n * ratio is not an integer
+int64_t resampler_out_len(const Resampler &r, int64_t n) { return (int64_t)std::ceil((double)n * r.ratio); }
 
 #define AMT_CUDA(call)                                                                                 \
     do {                                                                                               \
@@ -95,7 +99,8 @@ int64_t resampler_out_len(const Resampler &r, int64_t n) { return (int64_t)((dou
 int resampler_upload(Resampler &r, int device) {
     r.device = device;
     if (device < 0) return AMTFEAT_OK;
-    AMT_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    AMT_CUDA(guard.status);
     std::vector<double2> tab(r.win.size());
     for (size_t i = 0; i < tab.size(); ++i) tab[i] = make_double2(r.win[i], r.delta[i]);
     AMT_CUDA(cudaMalloc(reinterpret_cast<void **>(&r.d_tab), tab.size() * sizeof(double2)));
@@ -104,7 +109,7 @@ int resampler_upload(Resampler &r, int device) {
 }
 
 void resampler_free(Resampler &r) {
-    if (r.d_tab) { cudaSetDevice(r.device); cudaFree(r.d_tab); r.d_tab = nullptr; }
+    if (r.d_tab) { DeviceGuard guard(r.device); cudaFree(r.d_tab); r.d_tab = nullptr; }
 }
 
 struct IngestClip {
@@ -115,10 +120,16 @@ struct IngestClip {
 // float64 products); the wings read neighbouring input samples, which L1 / L2 serve.
 __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                        const IngestClip *__restrict__ clips, const double2 *__restrict__ tab,
-                                                       int nwin, int num_table, int index_step, double scale, double time_increment) {
+                                                       int nwin, int num_table, int index_step, double scale, double time_increment,
+                                                       double ratio) {
     const IngestClip c = clips[blockIdx.y];
     const float *x = in + c.in_off;
+    const long long n_res = (long long)((double)c.n_in * ratio);      // samples resampy itself produces; the rest is fix_length's zero padding
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < c.n_out; t += (long long)gridDim.x * blockDim.x) {
+        if (t >= n_res) {
+            out[c.out_off + t] = 0.f;
+            continue;
+        }
         const double time_register = (double)t * time_increment;
         const long long n = (long long)time_register;
         double acc = 0.0;
@@ -218,7 +229,7 @@ int resample_run(const Resampler &r, const float *d_in, const int64_t *in_off, c
     int rc = stage_clips(in_off, n_in, out_off, n_out.data(), batch, d_ws, ws_bytes, st, &d_clips, &d_acc);
     if (rc) return rc;
     dim3 grid(grid_for(maxo), batch);
-    resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_clips, r.d_tab, r.nwin, r.num_table, r.index_step, r.scale, 1.0 / r.ratio);
+    resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_clips, r.d_tab, r.nwin, r.num_table, r.index_step, r.scale, 1.0 / r.ratio, r.ratio);
     AMT_CUDA(cudaGetLastError());
     return AMTFEAT_OK;
 }

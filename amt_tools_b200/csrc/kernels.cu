@@ -20,6 +20,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "device_guard.h"
 #include "fft_device.cuh"
 #include "plan.h"
 
@@ -1622,27 +1623,9 @@ template <int NC> static int set_attrs() {
     return AMTFEAT_OK;
 }
 
-// Makes the plan's device current for the duration of a call and restores the caller's device afterwards: creating,
-// using or destroying a plan for cuda:k must not move the calling thread to cuda:k.
-struct DeviceGuard {
-    int prev = -1;
-    bool changed = false;
-    explicit DeviceGuard(int device) {
-        if (device < 0 || cudaGetDevice(&prev) != cudaSuccess) return;
-        if (prev != device) changed = cudaSetDevice(device) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (changed) cudaSetDevice(prev);
-    }
-};
-
 int upload_plan(Plan &p) {
     DeviceGuard guard(p.device);
-    {
-        int cur = -1;
-        AMT_CUDA(cudaGetDevice(&cur));
-        if (cur != p.device) AMT_CUDA(cudaSetDevice(p.device));   // reports an invalid ordinal
-    }
+    AMT_CUDA(guard.status);   // reports an invalid ordinal
     if (is_vqt_kind_cfg(p.cfg.kind)) {
         // highest priority: the ladder's few CTAs take the next free SM slots instead of queueing behind a projection grid
         int prio_lo = 0, prio_hi = 0;

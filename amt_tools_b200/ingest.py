@@ -73,7 +73,7 @@ class Resampler(object):
         return win, nt.value, step.value
 
     def __call__(self, audio):
-        """Resample one mono clip (N,) or a list of clips; returns CUDA tensors of length int(N * ratio)."""
+        """Resample one mono clip (N,) or a list of clips; returns CUDA tensors of length ceil(N * ratio) (librosa.resample, fix=True)."""
         if self.device is None:
             raise _lib.AmtfeatError('host-only resampler: no CUDA device (there is no CPU compute path)')
         single = not isinstance(audio, (list, tuple))

@@ -61,21 +61,35 @@ def synth_batch(sr, seconds, batch, seed0):
 # reference arm: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
 
-def _oracle_modules(spec):
+def _oracle_modules(spec, cache=None):
     from oracle import modules as om
     table = {'HCQT': om.OHCQT, 'MelSpec': om.OMelSpec, 'STFT': om.OSTFT, 'VQT': om.OVQT, 'CQT': om.OCQT,
              'SignalPower': om.OSignalPower}
-    return [(table[name](dtype=np.float32, **kw), sr) for name, kw, sr in spec]
+    mods = []
+    for name, kw, sr in spec:
+        kw = dict(kw, dtype=np.float32)
+        if cache is not None and name in ('HCQT', 'VQT', 'CQT'):
+            kw['basis_cache'] = cache
+        mods.append((table[name](**kw), sr))
+    return mods
 
 
 _AUDIO_CACHE = {}
+_BASIS_CACHE = {}
+_MODS_CACHE = {}
 
 
 def _oracle_worker(args):
-    wl, seconds, seed = args
+    """One pass of the oracle (float32, the precision the reference runs at) over one clip; returns the seconds it took.
+    cached=True keeps the wavelet bases of the process between calls (librosa rebuilds them on every call: 0.3 s, 1 % of a
+    240 s track but 12 % of a 20 s excerpt), so that the per-second cost of an excerpt equals that of a full track."""
+    wl, seconds, seed, cached = args
     from threadpoolctl import threadpool_limits
     from amt_tools_b200.synth import piano_like
-    mods = _oracle_modules(WORKLOADS[wl][1])
+    key = (wl, cached)
+    if key not in _MODS_CACHE:
+        _MODS_CACHE[key] = _oracle_modules(WORKLOADS[wl][1], _BASIS_CACHE if cached else None)
+    mods = _MODS_CACHE[key]
     for _, sr in mods:  # synthetic audio is generated once per worker process, outside the timed part
         if (sr, seconds) not in _AUDIO_CACHE:
             _AUDIO_CACHE[(sr, seconds)] = piano_like(int(round(sr * seconds)), sr, seed=seed)
@@ -87,8 +101,26 @@ def _oracle_worker(args):
 
 
 def cpu_sample_seconds(wl):
-    # bounded sample of the same workload: short clips of the same modules (CPU cost is linear in duration)
-    return {'c5': 20.0, 'c3': 20.0, 'c4': 30.0, 'c2': 20.0, 'c1': 30.0}[wl]
+    # bounded sample of the same workload: excerpts of the same tracks through the same modules (the cost is linear in the
+    # duration once the per-call basis construction is taken out, see _oracle_worker)
+    return {'c5': 20.0, 'c3': 30.0, 'c4': 30.0, 'c2': 20.0, 'c1': 30.0}[wl]
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: the same for both arms (the reference arm runs a bounded sample OF this workload)."""
+    desc, spec, seconds, default_batch = WORKLOADS[args.workload]
+    B = args.batch or default_batch
+    in_b = out_b = 0
+    for m, sr in _oracle_modules(spec):          # integer frame arithmetic only (features/common.py:41-66 and overrides)
+        n = int(round(sr * seconds))
+        in_b += 4 * B * n
+        out_b += 4 * B * m.num_channels * m.get_feature_size() * m.get_expected_frames(np.empty(n, dtype=np.float32))
+    return {'workload': args.workload + ': ' + desc, 'tracks_per_gpu_per_step': B, 'track_seconds': seconds,
+            'audio_hours_per_step': world * B * seconds / 3600.0,
+            'l2': 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) exceeds the 126 MB L2' % (in_b / 1e6, out_b / 1e6)
+                  if in_b + out_b > 126e6 else 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) fits the 126 MB L2: '
+                  'consecutive steps write fresh output buffers' % (in_b / 1e6, out_b / 1e6),
+            'parallelism': 'track-sharded x%d, no collective on the data path' % world}
 
 
 def run_reference(args):
@@ -96,26 +128,28 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))  # one single-threaded oracle process per host core (capped)
     sec = cpu_sample_seconds(args.workload)
     ctx = mp.get_context('fork')
     with ctx.Pool(procs) as pool:
         for _ in range(max(1, args.warmup)):
-            pool.map(_oracle_worker, [(args.workload, sec, 100 + i) for i in range(procs)], chunksize=1)
+            pool.map(_oracle_worker, [(args.workload, sec, 100 + i, True) for i in range(procs)], chunksize=1)
         t0 = time.perf_counter()
         for s in range(args.steps):
-            pool.map(_oracle_worker, [(args.workload, sec, 1000 * s + i) for i in range(procs)], chunksize=1)
+            pool.map(_oracle_worker, [(args.workload, sec, 100 + i, True) for i in range(procs)], chunksize=1)
         dt = time.perf_counter() - t0
     hours = args.steps * procs * sec / 3600.0
     value = hours / dt
-    wl = WORKLOADS[args.workload]
-    sample = '%d clips x %.0f s per step (one per process), oracle float32 port of the librosa algorithm' % (procs, sec)
+    sample = ('%d excerpts of %.0f s per step (one per host core) of the tracks of this workload, through the oracle float32 port of '
+              'the librosa algorithm; wavelet bases kept between calls so that the per-second cost equals that of a full %.0f s track '
+              '(librosa rebuilds them per call: 1 %% of a full track)' % (procs, sec, WORKLOADS[args.workload][2]))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'audio-hours/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload + ': ' + wl[0], 'sample': sample},
+        'config': workload_config(args, world),
         'cpu_baseline': {'value': value, 'unit': 'audio-hours/s', 'cores': procs, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'audio-hours/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -206,10 +240,12 @@ def kernel_algorithmic_bytes(mod, name, n):
         nfft = int(name[len('cqt_kernel_nfft'):]) if name != 'cqt_slide_kernel' else None
         total = 0
         for it in d['items']:
+            if it.get('alt'):
+                continue        # exact-ladder copies of a few rows: first / last frames only (tail_* launches)
             if (nfft is None and it.get('slide')) or (it['n_fft'] == nfft and not it.get('slide')):
                 total += 4 * int(np.ceil(n / 2.0 ** it['level'])) + 4 * it['rows'] * T
         return total
-    if name in ('decimate_kernel', 'decimate_fft_kernel'):
+    if name in ('decimate_kernel', 'decimate_fft_kernel', 'decimate_fft64_kernel'):
         return sum(4 * int(np.ceil(n / 2.0 ** (l - 1))) + 4 * int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
     if name == 'db_epilogue_kernel':
         return 8 * mod.get_num_channels() * mod.get_feature_size() * T
@@ -242,19 +278,131 @@ def algorithmic_flops(mod, n):
         # FFT-per-frame items: the SURVEY model; sliding-DFT items (deep levels) as executed: per band bin and frame
         # 4 hop flops for the entering / leaving samples + 44 for the phase bookkeeping, times the tile lead-in overhead
         fft = 0.0
-        for it in d['items']:
+        main = [it for it in d['items'] if not it.get('alt')]     # the exact-ladder copies cover a few hundred frames of a clip: not counted
+        for it in main:
             kb = it['kmax_padded'] - it['kmin'] + 1
             if it.get('slide'):
                 tile = min(1024, 4096 // it['hop'])
                 fft += kb * (4.0 * it['hop'] + 44.0) * (1.0 + (it['n_fft'] // it['hop']) / float(tile))
             else:
                 fft += 2.5 * it['n_fft'] * np.log2(it['n_fft']) + 3.0 * (it['kmax'] - it['kmin'] + 1)
-        uniq = sum(it['unique_rows'] for it in d['items']) / max(1, sum(it['rows'] for it in d['items']))
+        uniq = sum(it['unique_rows'] for it in main) / max(1, sum(it['rows'] for it in main))
         proj = 8.0 * d['basis_nnz'] * uniq
         dec_out = sum(int(np.ceil(n / 2.0 ** l)) for l in range(1, d['n_levels']))
-        dec = dec_out * (111.0 if d.get('decimator') == 'fft' else 2.0 * d['decim_taps'])
+        # fast-convolution forms as executed: float32 ~111 flop per output, float64 (default) ~107 (2048-point complex forward, spectral
+        # product, fold, 1024-point inverse per 2 x 830 outputs) -- float64 operations counted like float32 ones
+        dec = dec_out * (111.0 if d.get('decimator') == 'fft32' else 107.0 if d.get('decimator') == 'fft64' else 2.0 * d['decim_taps'])
         return T * (fft + proj + db) + dec
     return 0.0
+
+
+def device_leg(ab, torch, dist, dev, wl, world, rank, steps, batch=None):
+    """Device-resident throughput of one more named workload (BASELINE.json configs[1..3]): same stepping as the main leg
+    (one stream per module, consecutive steps alternating between two stream sets), its own synthetic batch per rank."""
+    desc, spec, seconds, default_batch = WORKLOADS[wl]
+    B = batch or default_batch
+    mods, audio = [], []
+    for i, (name, kw, sr) in enumerate(spec):
+        mods.append(getattr(ab, name)(device=dev, **kw))
+        audio.append(torch.from_numpy(synth_batch(sr, seconds, B, seed0=7000 + 1000 * rank + 10 * i)).to(dev))
+    n_per = [int(a.shape[1]) for a in audio]
+    # L2 hygiene: the inputs rotate over enough copies that a step never finds its audio in the 126 MB L2, and the outputs of the
+    # last `ncopy` steps stay alive so that the allocator hands out memory that has left the L2 as well
+    in_bytes = sum(4 * a.numel() for a in audio)
+    ncopy = max(2, int(np.ceil(3 * 126e6 / max(in_bytes, 1))))
+    copies = [[a.clone() for a in audio] for _ in range(min(ncopy, 32))]
+    sets = [[torch.cuda.Stream(dev) for _ in mods] for _ in range(2)]
+    cur = torch.cuda.current_stream(dev)
+    count = [0]
+    alive = []
+
+    def step():
+        ss = sets[count[0] % 2]
+        cp = copies[count[0] % len(copies)]
+        count[0] += 1
+        outs = []
+        for m, a, st in zip(mods, cp, ss):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(m.process_audio(a))
+        alive.append(outs)
+        if len(alive) > len(copies):
+            alive.pop(0)
+        return outs
+
+    def join():
+        for ss in sets:
+            for st in ss:
+                cur.wait_stream(st)
+
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or time.perf_counter() - t0 < 0.2:
+        step()
+        n += 1
+        if n % 8 == 0:
+            torch.cuda.synchronize()
+    join()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    join()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    step_bytes = sum(B * algorithmic_bytes(m, n) for m, n in zip(mods, n_per))
+    step_flops = sum(B * algorithmic_flops(m, n) for m, n in zip(mods, n_per))
+    return {'workload': wl + ': ' + desc, 'tracks_per_gpu_per_step': B, 'value': world * B * seconds / 3600.0 / (ms_step * 1e-3),
+            'ms_per_step': ms_step, 'algorithmic_bytes_per_step': step_bytes, 'algorithmic_flops_per_step': step_flops,
+            'l2': 'inputs rotate over %d device copies (%.0f MB) and the outputs of the last %d steps stay allocated: no step finds '
+                  'its data in the 126 MB L2' % (len(copies), len(copies) * in_bytes / 1e6, len(copies))}
+
+
+def leg_fractions(r, sm_mhz, hbm_peak):
+    """Fractions of the two rooflines for one workload leg: algorithmic bytes over the measured HBM peak, algorithmic flops over
+    the FP32 FMA peak at the observed SM clock; the binding one is the larger time."""
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
+    t_hbm = r['algorithmic_bytes_per_step'] / (hbm_peak * 1e9) * 1e3
+    t_fp32 = r['algorithmic_flops_per_step'] / fp32_peak * 1e3
+    r.update(hbm_frac=t_hbm / r['ms_per_step'], fp32_frac=t_fp32 / r['ms_per_step'], roofline_ms=max(t_hbm, t_fp32),
+             roofline_frac=max(t_hbm, t_fp32) / r['ms_per_step'], bound='hbm' if t_hbm >= t_fp32 else 'fp32')
+    return r
+
+
+def cache_leg(ab, torch, dev, spec, seconds, tracks, compressed, writers):
+    """The caller BASELINE.json configs[4] names, end to end: TranscriptionDataset's feature precompute (datasets/common.py:212-295:
+    compute -> np.savez(_compressed) -> <save_loc>/<Dataset>/<features_name()>/<track>.npz) through precompute_features."""
+    import shutil
+    from amt_tools_b200 import precompute
+    from amt_tools_b200.synth import piano_like
+    root = tempfile.mkdtemp(prefix='amtfeat_cache_')
+    try:
+        t_total, nbytes, stats_all = 0.0, 0, []
+        for name, kw, sr in spec:
+            m = getattr(ab, name)(device=dev, **kw)
+            uniq = [piano_like(int(round(sr * seconds)), sr, seed=9000 + i) for i in range(2)]
+            corpus = {'track_%04d' % i: uniq[i % 2] for i in range(tracks)}
+            m.process_audio(uniq[0][:sr * 2])          # plan creation / first-launch costs stay outside the timed part
+            torch.cuda.synchronize()
+            stats = {}
+            t = time.perf_counter()
+            out = precompute.precompute_features(corpus, m, root, 'Synth', compressed=compressed, writers=writers, stats=stats)
+            t_total += time.perf_counter() - t
+            nbytes += sum(os.path.getsize(p) for p in out.values())
+            stats_all.append(dict(stats, module=name))
+        return {'value': tracks * seconds / 3600.0 / t_total, 'unit': 'audio-hours/s', 'tracks': tracks, 'seconds': t_total,
+                'bytes_written': nbytes, 'write_GBps': nbytes / t_total / 1e9, 'compressed': bool(compressed), 'writers': writers,
+                'dir': root, 'stages': stats_all}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 def run_ours(args):
@@ -499,9 +647,23 @@ def run_ours(args):
             'path': 'FeatureModule.process_audio (Python API): pinned host audio -> H2D -> kernels; features stay on the '
                     'device for the model, one float per track and module read back', 'checksum': float(last.sum()),
         }
+    # ---------------- the other named shapes (BASELINE.json configs[1..3]), device resident, same run ----------------
+    extra = None
+    if args.workload == 'c5' and not args.no_extra:
+        extra = {}
+        for wl in ('c2', 'c3', 'c4'):
+            extra[wl] = device_leg(ab, torch, dist, dev, wl, world, rank, max(5, min(args.steps, 20)))
+    # ---------------- the configs[4] caller end to end: precompute + npz cache (one GPU only: every rank would hit one disk) ----
+    cache = None
+    if args.workload == 'c5' and world == 1 and not args.no_cache and not args.no_e2e:
+        writers = max(1, min(16, (os.cpu_count() or 2) - 1))
+        cache = {'savez': cache_leg(ab, torch, dev, spec, seconds, args.cache_tracks, False, writers),
+                 'savez_compressed': cache_leg(ab, torch, dev, spec, seconds, max(2, args.cache_tracks // 4), True, writers),
+                 'note': 'precompute_features (amtfeat_pipeline_* + writer threads): every track through HCQT and MelSpec, one .npz per '
+                         'track and module in the reference cache layout; np.savez_compressed is the reference default and is bound by zlib on the host cores'}
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks['window'] = 'warm-up + device-timed steps + e2e steps (nvidia-smi -lms 50)'
+        clocks['window'] = 'warm-up + device-timed steps + e2e steps + the other workloads (nvidia-smi -lms 50)'
 
     if rank != 0:
         if world > 1:
@@ -533,7 +695,7 @@ def run_ours(args):
     # measured DRAM traffic per launch of that kernel (ncu --set full capture of this workload, profiles/r01_traffic.json)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))['traffic_bytes_per_launch']
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json' if os.path.exists(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) else 'r01_traffic.json')))['traffic_bytes_per_launch']
         ncu_name = {'cqt_kernel_nfft1024': 'void cqt_kernel<512, 1>(CqtParams)', 'cqt_kernel_nfft512': 'void cqt_kernel<256, 1>(CqtParams)',
                     'cqt_slide_kernel': 'cqt_slide_kernel(SlideParams)',
                     'stft_kernel_mel': 'void stft_kernel<1024, 1>(StftParams)'}.get(top[0].split('.')[1])
@@ -575,29 +737,40 @@ def run_ours(args):
                         'model': 'SURVEY.md 8(d) algorithmic flops (FFT 2.5 n log2 n, sparse projections; sliding-DFT items '
                                  'and decimator as executed); peak = 148 SMs x 128 FMA lanes x 2 x %.0f MHz' % sm_mhz}
 
+    if extra:
+        for r in extra.values():
+            leg_fractions(r, sm_mhz, hbm_peak)
     cpu = None
     if not args.no_cpu:
-        sec = cpu_sample_seconds(args.workload)
-        t = _oracle_worker((args.workload, sec, 77))
+        sec = seconds            # one full track / clip of this very workload, bases rebuilt per call like librosa does
+        t = _oracle_worker((args.workload, sec, 77, False))
         cpu = {'value': sec / 3600.0 / t, 'unit': 'audio-hours/s', 'cores': 1, 'kind': 'port',
-               'sample': 'one %.0f s clip through the oracle float32 port of the same modules (%.1f s of CPU)' % (sec, t)}
+               'sample': 'one full %.0f s track of this workload through the oracle float32 port of the same modules (%.1f s of CPU)' % (sec, t)}
 
     launches = sum(int(_lib.lib.amtfeat_launch_count(m._dev_plan.handle, B, _lib.i64_array([n] * B)))
                    for m, n in zip(mods, n_per))
+    flat = {'fp32_frac': roofline['fp32']['frac'], 'hbm_frac': roofline['frac'],
+            'step_traffic_ratio': roofline.get('step_traffic_ratio'),
+            'e2e_device_value': (e2e or {}).get('device_consumer', {}).get('value') if e2e else None}
+    if extra:
+        for wl, r in extra.items():
+            for k in ('value', 'ms_per_step', 'hbm_frac', 'fp32_frac', 'roofline_frac'):
+                flat['%s_%s' % (wl, k)] = r[k]
+    if cache is not None:
+        flat['e2e_cache_value'] = cache['savez']['value']
+        flat['e2e_cache_compressed_value'] = cache['savez_compressed']['value']
     line = {
         'metric': METRIC, 'value': value, 'unit': 'audio-hours/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': args.workload + ': ' + desc, 'tracks_per_gpu_per_step': B, 'track_seconds': seconds,
-                   'audio_hours_per_step': world * hours_per_step,
-                   'l2': 'per-step working set (inputs %.0f MB + outputs %.0f MB per GPU) exceeds the 126 MB L2'
-                         % (sum(4 * B * n for n in n_per) / 1e6, (step_bytes - sum(4 * B * n for n in n_per)) / 1e6),
-                   'parallelism': 'track-sharded x%d, no collective on the data path' % world,
-                   'host_binding': ('rank pinned to the %d CPU cores next to its GPU (NVML affinity)' % len(numa_cpus)) if numa_cpus else 'none',
-                   'streams': ('one CUDA stream per module, consecutive steps alternate between two stream sets (joined at the end of the timed region)'
-                               if step_sets else 'one CUDA stream per module, joined every step' if mod_streams else 'single stream')},
+        'config': workload_config(args, world),
+        'run_config': {'host_binding': ('rank pinned to the %d CPU cores next to its GPU (NVML affinity)' % len(numa_cpus)) if numa_cpus else 'none',
+                       'streams': ('one CUDA stream per module, consecutive steps alternate between two stream sets (joined at the end of the timed region)'
+                                   if step_sets else 'one CUDA stream per module, joined every step' if mod_streams else 'single stream')},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
+        'workloads': extra, 'cache': cache,
     }
+    line.update(flat)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -633,6 +806,9 @@ def main():
     ap.add_argument('--serial-steps', action='store_true', help='join every step on the current stream (A/B for the step pipelining)')
     ap.add_argument('--no-bind', action='store_true', help='do not pin the rank to the CPU cores next to its GPU (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the device-resident legs of the other named workloads (c2, c3, c4)')
+    ap.add_argument('--no-cache', action='store_true', help='skip the precompute + npz cache leg')
+    ap.add_argument('--cache-tracks', type=int, default=16, help='tracks of the precompute + cache leg (np.savez; a quarter of them compressed)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

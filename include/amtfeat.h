@@ -185,7 +185,7 @@ enum { AMTFEAT_RES_KAISER_BEST = 0, AMTFEAT_RES_KAISER_FAST = 1 };
 typedef struct amtfeat_resampler amtfeat_resampler;
 AMTFEAT_API int amtfeat_resampler_create(double sr_orig, double sr_new, int filter, int device, amtfeat_resampler **out);
 AMTFEAT_API void amtfeat_resampler_destroy(amtfeat_resampler *r);
-/* int(num_samples * sr_new / sr_orig), the output length resampy allocates */
+/* ceil(num_samples * sr_new / sr_orig): librosa.resample(fix=True) pads resampy's int(n * ratio) samples with zeros to that length */
 AMTFEAT_API int64_t amtfeat_resampler_out_len(const amtfeat_resampler *r, int64_t num_samples);
 /* Copies up to `capacity` entries of the half window (scaled by the ratio when downsampling); returns its length.
  * num_table = table samples per zero crossing, index_step = stride per input sample (either may be NULL). */

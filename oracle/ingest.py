@@ -34,7 +34,8 @@ def sinc_window(num_zeros, precision, beta, rolloff):
 def resample(x, sr_orig, sr_new, res_type='kaiser_best'):
     x = np.asarray(x)
     ratio = float(sr_new) / sr_orig
-    n_out = int(x.shape[-1] * ratio)
+    n_out = int(x.shape[-1] * ratio)                # resampy.resample: shape[axis] = int(shape[axis] * sample_ratio)
+    n_fix = int(np.ceil(x.shape[-1] * ratio))       # librosa.resample(fix=True): util.fix_length(y_hat, size=ceil(n * ratio))
     interp_win, num_table, _ = sinc_window(*FILTERS[res_type])
     if ratio < 1:
         interp_win = ratio * interp_win
@@ -62,6 +63,7 @@ def resample(x, sr_orig, sr_new, res_type='kaiser_best'):
         k_max = min(n_orig - n - 1, (nwin - offset) // index_step)
         idx = offset + np.arange(k_max) * index_step
         y[t] += np.dot(interp_win[idx] + eta * interp_delta[idx], xd[n + 1 + np.arange(k_max)])
+    y = np.concatenate([y, np.zeros(n_fix - n_out)])     # fix_length pads with zeros
     return y.astype(x.dtype if x.dtype.kind == 'f' else np.float64)
 
 
