@@ -807,14 +807,18 @@ struct TailParams {
     const ClipMeta *meta;
     const double *taps;
     int ntaps, factor, level_in, level_out, alt, head;   // head: the head piece [0, alt_hlen) instead of the tail piece [alt_first, len)
-    int taps_smem;                                       // the taps fit in shared memory next to the staged input
 };
 
-// A CTA produces kThreads consecutive outputs.  Polyphase form: tap k = F q + ph of output m reads x[F (m - q) + D - ph], so the
-// input span is staged in shared memory de-interleaved by phase, as float64: X[ph][j] = x[F (m0 + j - nq + 1) + D - ph].  The
-// inner loop is then one conflict-free 8-byte load, one broadcast tap load and one float64 FMA per tap (FP64-pipe bound).
+// A CTA produces kTailOut = 4 x kThreads consecutive outputs, four per thread (64 apart: conflict-free shared-memory reads that
+// share every tap load).  Polyphase form: tap k = F q + ph of output m reads x[F (m - q) + D - ph], so the input span is staged
+// in shared memory de-interleaved by phase: X[ph][j] = x[F (m0 + j - nq + 1) + D - ph].  Products of four taps are summed in
+// float32 (exact products of float32 data and float32-rounded taps, three additions) and folded into a float64 accumulator:
+// the result carries one float32 rounding per 4 taps of its 4-tap partial sums and none from the long summation -- as good as
+// the final rounding to float32 -- at a quarter of the float64 operations and shared-memory wavefronts of a plain float64 loop.
+constexpr int kTailPerThread = 4, kTailOut = kTailPerThread * kThreads;
+
 __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
-    extern __shared__ __align__(16) double tsm[];
+    extern __shared__ __align__(16) float tsm[];
     const ClipMeta *cm = p.meta + blockIdx.y;
     long long first, end;
     float *dst;
@@ -830,7 +834,7 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         end = cm->lvl_len[p.level_out];
         dst = p.ladder + cm->alt_off[p.alt][p.level_out];
     }
-    const long long m0 = first + (long long)blockIdx.x * kThreads;
+    const long long m0 = first + (long long)blockIdx.x * kTailOut;
     if (m0 >= end) return;
     const float *src;
     long long lo, hi;   // samples of the input piece that exist; everything outside reads as zero (true for < 0 and >= len; the
@@ -849,39 +853,38 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         hi = cm->lvl_len[p.level_in];
     }
     const int F = p.factor, D = (p.ntaps - 1) / 2;
-    const int nq = (p.ntaps + F - 1) / F;          // taps per phase
-    const int J = kThreads + nq - 1, JP = J | 1;   // entries per phase (odd pitch)
-    double *X = tsm, *hs = tsm + (size_t)F * JP;   // hs[ph * nq + q] = taps[F q + ph]
-    if (p.taps_smem)
-        for (int i = threadIdx.x; i < F * nq; i += kThreads) {
-            const int ph = i / nq, q = i - ph * nq, k = F * q + ph;
-            hs[i] = k < p.ntaps ? __ldg(p.taps + k) : 0.0;
-        }
+    const int nq = ((p.ntaps + F - 1) / F + 3) & ~3;      // taps per phase, padded to a multiple of 4 with zeros
+    const int J = kTailOut + nq - 1, JP = J | 1;          // entries per phase (odd pitch)
+    float *hs = tsm, *X = tsm + (size_t)F * nq;           // hs[ph * nq + q] = taps[F q + ph] (16-byte aligned rows: float4 loads)
+    for (int i = threadIdx.x; i < F * nq; i += kThreads) {
+        const int ph = i / nq, q = i - ph * nq, k = F * q + ph;
+        hs[i] = k < p.ntaps ? (float)__ldg(p.taps + k) : 0.f;
+    }
     const long long g0 = (long long)F * (m0 - nq + 1) + D;     // X[ph][j] = x[g0 + F j - ph]
     for (int i = threadIdx.x; i < F * J; i += kThreads) {
         const int u = i - (F - 1);                                // u = F j - ph, -(F - 1) <= u <= F (J - 1)
         const int ph = (F - 1) - ((u + F - 1) % F), j = (u + ph) / F;
         const long long g = g0 + u;
-        X[ph * JP + j] = (g >= lo && g < hi) ? (double)src[g] : 0.0;
+        X[ph * JP + j] = (g >= lo && g < hi) ? src[g] : 0.f;
     }
     __syncthreads();
-    const long long m = m0 + threadIdx.x;
-    if (m >= end) return;
-    double a0 = 0.0, a1 = 0.0;
+    double acc[kTailPerThread] = {0.0, 0.0, 0.0, 0.0};
     for (int ph = 0; ph < F; ++ph) {
-        const double *xp = X + ph * JP + threadIdx.x + nq - 1, *hp = hs + ph * nq;
-        if (p.taps_smem) {
-            int q = 0;
-            for (; q + 1 < nq; q += 2) {
-                a0 = fma(hp[q], xp[-q], a0);
-                a1 = fma(hp[q + 1], xp[-q - 1], a1);
+        const float *xp = X + ph * JP + threadIdx.x + nq - 1, *hp = hs + ph * nq;
+        for (int q = 0; q < nq; q += 4) {
+            const float4 h4 = *reinterpret_cast<const float4 *>(hp + q);
+#pragma unroll
+            for (int r = 0; r < kTailPerThread; ++r) {
+                const float *x = xp + r * kThreads - q;
+                acc[r] += (double)(fmaf(h4.x, x[0], h4.y * x[-1]) + fmaf(h4.z, x[-2], h4.w * x[-3]));
             }
-            if (q < nq) a0 = fma(hp[q], xp[-q], a0);
-        } else {     // very long one-shot filters (2^eds >= 32): taps straight from global memory (warp-uniform loads)
-            for (int q = 0; F * q + ph < p.ntaps; ++q) a0 = fma(__ldg(p.taps + F * q + ph), xp[-q], a0);
         }
     }
-    dst[m] = (float)(a0 + a1);
+#pragma unroll
+    for (int r = 0; r < kTailPerThread; ++r) {
+        const long long m = m0 + threadIdx.x + r * kThreads;
+        if (m < end) dst[m] = (float)acc[r];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2243,11 +2246,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                     }
                     if (count <= 0) continue;
                     tp.head = head;
-                    dim3 grid((count + kThreads - 1) / kThreads, batch);
-                    const int nq = (tp.ntaps + tp.factor - 1) / tp.factor;
-                    const size_t xbytes = (size_t)tp.factor * ((kThreads + nq - 1) | 1) * sizeof(double), hbytes = (size_t)tp.factor * nq * sizeof(double);
-                    tp.taps_smem = xbytes + hbytes <= 200 * 1024;
-                    const size_t tsmem = xbytes + (tp.taps_smem ? hbytes : 0);
+                    dim3 grid((count + kTailOut - 1) / kTailOut, batch);
+                    const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
+                    const size_t tsmem = ((size_t)tp.factor * ((kTailOut + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
                     if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
                     ProfScope ps(p, "tail_decimate_kernel", lst);
                     tail_decimate_kernel<<<grid, kThreads, tsmem, lst>>>(tp);

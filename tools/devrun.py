@@ -5,7 +5,7 @@ import sys
 
 wls = sys.argv[1:] or ['c5', 'c2', 'c4']
 for wl in wls:
-    out = subprocess.run([sys.executable, 'bench.py', '--workload', wl, '--steps', '10', '--no-e2e', '--no-cpu'],
+    out = subprocess.run([sys.executable, 'bench.py', '--workload', wl, '--steps', '10', '--no-e2e', '--no-cpu', '--no-extra', '--no-cache'],
                          capture_output=True, text=True)
     try:
         j = json.loads(out.stdout.strip().splitlines()[-1])
