@@ -530,8 +530,8 @@ static int build_vqt(Plan &p) {
                 p.decim_h64[2 * k] = v.real();
                 p.decim_h64[2 * k + 1] = v.imag();
             }
-            // per-pass twiddle tables of its Stockham transforms (kernels.cu stockham_pass): radix-4 passes with
-            // sub-transform size Ns = 4, 16, 64, 256: [r - 1][k] = exp(-2 pi i r k / (4 Ns)); then the radix-2 pass, Ns = 1024
+            // per-pass twiddle tables of its Stockham transforms (kernels.cu decimate_fft64_kernel), each [r - 1][k] =
+            // exp(-2 pi i r k / (R Ns)), k < Ns: forward 2048 = 16 x 16 x 8 (passes B, C), inverse 1024 = 8 x 8 x 16 (passes E, F)
             p.decim_tw64.clear();
             auto push_tw = [&](long long num, long long den) {   // exp(-2 pi i num / den), exact at the octant points
                 num %= den;
@@ -545,10 +545,14 @@ static int build_vqt(Plan &p) {
                 p.decim_tw64.push_back(c);
                 p.decim_tw64.push_back(sn);
             };
-            for (int Ns = 4; Ns <= 256; Ns *= 4)
-                for (int r = 1; r < 4; ++r)
-                    for (int k = 0; k < Ns; ++k) push_tw((long long)r * k, 4ll * Ns);
-            for (int k = 0; k < 1024; ++k) push_tw(k, 2048);
+            auto push_pass = [&](int R, int Ns) {
+                for (int r = 1; r < R; ++r)
+                    for (int k = 0; k < Ns; ++k) push_tw((long long)r * k, (long long)R * Ns);
+            };
+            push_pass(16, 16);    // B:  240 entries at 0
+            push_pass(8, 256);    // C: 1792 entries at 240
+            push_pass(8, 8);      // E:   56 entries at 2032
+            push_pass(16, 64);    // F:  960 entries at 2088
         }
     }
 

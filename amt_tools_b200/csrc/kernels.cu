@@ -681,14 +681,13 @@ __global__ void __launch_bounds__(kDfThreads, 2) decimate_fft_kernel(const DecFf
 //   a float64 table; ~100 float64 flop per output sample.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kD64Threads = 256;
-constexpr int kD64Buf = 2048 + 2048 / 8;   // one padded buffer (double2)
+constexpr int kD64Threads = 128;
 
 struct Dec64Params {
     const float *audio;
     float *ladder;
     const ClipMeta *meta;
-    const double2 *tw;   // per-pass twiddle tables (host_plan.cpp decim_tw64): radix 4, Ns = 4, 16, 64, 256: [r - 1][k]; radix 2, Ns = 1024: [k]
+    const double2 *tw;   // per-pass twiddle tables (host_plan.cpp decim_tw64), see tw64_off
     const double2 *H;    // response of the taps, k < 2048, times 1 / 2048
     int level_out, D, M, pairs_per_cta;
 };
@@ -698,45 +697,66 @@ __device__ __forceinline__ double2 dmul(double2 a, double2 b) {
 }
 __device__ __forceinline__ double2 dadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 dsub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-// One extra 16-byte slot per 8: the stride-4 stores of the first radix-4 pass (and the stride-2 ones of the last pass) spread over
-// all eight 16-byte bank groups instead of two.
-__device__ __forceinline__ int ph64(int i) { return i + (i >> 3); }
-__host__ __device__ constexpr int tw64_off(int Ns) { return Ns == 4 ? 0 : Ns == 16 ? 12 : Ns == 64 ? 60 : Ns == 256 ? 252 : 1020; }
 
-// One Stockham pass of an N-point forward DFT (radix R, sub-transform size Ns so far): thread j takes inputs j + r N / R,
-// twiddles them by exp(-2 pi i r (j mod Ns) / (Ns R)), and writes the R-point DFT to (j / Ns) Ns R + (j mod Ns) + r Ns.
-template <int N, int R, int Ns>
-__device__ __forceinline__ void stockham_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw, int tid) {
-    const double2 *twp = tw + tw64_off(Ns);
+// exp(-2 pi i m / 32), m = 0..15, float64
+__device__ __forceinline__ double2 w32d(int m) {
+    switch (m) {
+        case 0: return make_double2(1.0, -0.0);
+        case 1: return make_double2(0.98078528040323043, -0.19509032201612825);
+        case 2: return make_double2(0.92387953251128674, -0.38268343236508978);
+        case 3: return make_double2(0.83146961230254524, -0.55557023301960218);
+        case 4: return make_double2(0.70710678118654757, -0.70710678118654757);
+        case 5: return make_double2(0.55557023301960218, -0.83146961230254524);
+        case 6: return make_double2(0.38268343236508978, -0.92387953251128674);
+        case 7: return make_double2(0.19509032201612825, -0.98078528040323043);
+        case 8: return make_double2(0.0, -1.0);
+        case 9: return make_double2(-0.19509032201612825, -0.98078528040323043);
+        case 10: return make_double2(-0.38268343236508978, -0.92387953251128674);
+        case 11: return make_double2(-0.55557023301960218, -0.83146961230254524);
+        case 12: return make_double2(-0.70710678118654757, -0.70710678118654757);
+        case 13: return make_double2(-0.83146961230254524, -0.55557023301960218);
+        case 14: return make_double2(-0.92387953251128674, -0.38268343236508978);
+        default: return make_double2(-0.98078528040323043, -0.19509032201612825);
+    }
+}
+
+// In-register forward DFT of R points, float64 (radix-2 decimation in frequency; output k lives in register brev<R>(k)).
+template <int R> __device__ __forceinline__ void dft_regs(double2 (&v)[R]) {
 #pragma unroll
-    for (int j = tid; j < N / R; j += kD64Threads) {
-        const int k = j & (Ns - 1);
-        double2 v[R];
+    for (int half = R / 2; half >= 1; half >>= 1) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[ph64(j + r * (N / R))];
-        if (Ns > 1) {
+        for (int blk = 0; blk < R; blk += 2 * half) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = dmul(v[r], __ldg(twp + (r - 1) * Ns + k));
-        }
-        const int j0 = (j - k) * R + k;
-        if (R == 4) {
-            const double2 a = dadd(v[0], v[2]), b = dsub(v[0], v[2]), c = dadd(v[1], v[3]), d = dsub(v[1], v[3]);
-            const double2 dmi = make_double2(d.y, -d.x);   // -i d
-            out[ph64(j0)] = dadd(a, c);
-            out[ph64(j0 + Ns)] = dadd(b, dmi);
-            out[ph64(j0 + 2 * Ns)] = dsub(a, c);
-            out[ph64(j0 + 3 * Ns)] = dsub(b, dmi);
-        } else {
-            out[ph64(j0)] = dadd(v[0], v[1]);
-            out[ph64(j0 + Ns)] = dsub(v[0], v[1]);
+            for (int j = 0; j < half; ++j) {
+                const double2 a = v[blk + j], b = v[blk + j + half];
+                v[blk + j] = dadd(a, b);
+                const double2 d = dsub(a, b);
+                const int m = j * (16 / half);  // twiddle exp(-2 pi i j / (2 half)) = w32d(m)
+                if (m == 0) v[blk + j + half] = d;
+                else if (m == 8) v[blk + j + half] = make_double2(d.y, -d.x);
+                else if (m == 4) v[blk + j + half] = make_double2((d.x + d.y) * 0.70710678118654757, (d.y - d.x) * 0.70710678118654757);
+                else if (m == 12) v[blk + j + half] = make_double2((d.y - d.x) * 0.70710678118654757, -(d.x + d.y) * 0.70710678118654757);
+                else v[blk + j + half] = dmul(d, w32d(m));
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kD64Threads, 3) decimate_fft64_kernel(const Dec64Params p) {
-    extern __shared__ __align__(16) double2 smem64[];
-    double2 *b0 = smem64, *b1 = b0 + kD64Buf;
-    const int tid = threadIdx.x;
+// Twiddle tables of the passes below, each [r - 1][k] = exp(-2 pi i r k / (R Ns)), k < Ns:
+//   forward 2048 = 16 x 16 x 8:  pass B (R 16, Ns 16) at 0 (240 entries), pass C (R 8, Ns 256) at 240 (1792)
+//   inverse 1024 = 8 x 8 x 16:   pass E (R 8, Ns 8) at 2032 (56), pass F (R 16, Ns 64) at 2088 (960)
+constexpr int kTw64B = 0, kTw64C = 240, kTw64E = 2032, kTw64F = 2088, kTw64Total = 3048;
+// shared-memory index padding: one extra 16-byte slot per 16 (forward) / per 8 (inverse) entries, so that the strided stores of
+// a pass (thread j writes entries 16 j + r, or 8 t + s) spread over all eight 16-byte bank groups
+__device__ __forceinline__ int pf64(int i) { return i + (i >> 4); }
+__device__ __forceinline__ int pi64(int i) { return i + (i >> 3); }
+constexpr int kD64Buf = 2048 + 2048 / 16;   // double2 entries of the one (in-place) buffer
+
+// One CTA (128 threads, 16 complex float64 values per thread) per pair of blocks: every pass is one register-resident radix-16 /
+// radix-8 DFT per thread with the Stockham index map; the data crosses shared memory twice per transform, in place.
+__global__ void __launch_bounds__(kD64Threads, 4) decimate_fft64_kernel(const Dec64Params p) {
+    extern __shared__ __align__(16) double2 buf[];
+    const int t = threadIdx.x;
     const ClipMeta *cm = p.meta + blockIdx.y;
     const int len_out = cm->lvl_len[p.level_out], len_in = cm->lvl_len[p.level_out - 1];
     const int npairs = (int)(((long long)len_out + 2 * p.M - 1) / (2 * p.M));
@@ -748,48 +768,100 @@ __global__ void __launch_bounds__(kD64Threads, 3) decimate_fft64_kernel(const De
     for (int pair = pair0; pair < pair1; ++pair) {
         const long long mA = (long long)pair * 2 * p.M, mB = mA + p.M;
         const bool haveB = mB < len_out;
-        const long long baseA = 2 * mA - p.D, baseB = 2 * mB - p.D;      // even: D is even
+        const long long baseA = 2 * mA - p.D, baseB = 2 * mB - p.D;
         const bool interior = baseA >= 0 && baseB + 2048 <= len_in;
-        if (pair != pair0) __syncthreads();   // the previous pair's result has been read
-        for (int n = 2 * tid; n < 2048; n += 2 * kD64Threads) {
-            float2 xa, xb;
+        double2 v[16];
+        // ---- forward 2048, pass A (radix 16, Ns = 1): z[t + 128 r] = uA + i uB straight from global memory
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int n = t + 128 * r;
+            float xa, xb;
             if (interior) {
-                xa = __ldg(reinterpret_cast<const float2 *>(src + baseA + n));
-                xb = __ldg(reinterpret_cast<const float2 *>(src + baseB + n));
+                xa = __ldg(src + baseA + n);
+                xb = __ldg(src + baseB + n);
             } else {
                 const long long ia = baseA + n, ib = baseB + n;
-                xa.x = (ia >= 0 && ia < len_in) ? __ldg(src + ia) : 0.f;
-                xa.y = (ia + 1 >= 0 && ia + 1 < len_in) ? __ldg(src + ia + 1) : 0.f;
-                xb.x = (haveB && ib >= 0 && ib < len_in) ? __ldg(src + ib) : 0.f;
-                xb.y = (haveB && ib + 1 >= 0 && ib + 1 < len_in) ? __ldg(src + ib + 1) : 0.f;
+                xa = (ia >= 0 && ia < len_in) ? __ldg(src + ia) : 0.f;
+                xb = (haveB && ib >= 0 && ib < len_in) ? __ldg(src + ib) : 0.f;
             }
-            b0[ph64(n)] = make_double2((double)xa.x, (double)xb.x);
-            b0[ph64(n + 1)] = make_double2((double)xa.y, (double)xb.y);
+            v[r] = make_double2((double)xa, (double)xb);
+        }
+        dft_regs<16>(v);
+        if (pair != pair0) __syncthreads();          // the previous pair's last reads of the buffer are done
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf[pf64(16 * t + r)] = v[brev<16>(r)];
+        __syncthreads();
+        // ---- pass B (radix 16, Ns = 16)
+        {
+            const int k = t & 15;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = buf[pf64(t + 128 * r)];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) v[r] = dmul(v[r], __ldg(p.tw + kTw64B + (r - 1) * 16 + k));
+            dft_regs<16>(v);
+            __syncthreads();
+            const int j0 = (t - k) * 16 + k;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) buf[pf64(j0 + 16 * r)] = v[brev<16>(r)];
         }
         __syncthreads();
-        stockham_pass<2048, 4, 1>(b0, b1, p.tw, tid);    __syncthreads();
-        stockham_pass<2048, 4, 4>(b1, b0, p.tw, tid);    __syncthreads();
-        stockham_pass<2048, 4, 16>(b0, b1, p.tw, tid);   __syncthreads();
-        stockham_pass<2048, 4, 64>(b1, b0, p.tw, tid);   __syncthreads();
-        stockham_pass<2048, 4, 256>(b0, b1, p.tw, tid);  __syncthreads();
-        stockham_pass<2048, 2, 1024>(b1, b0, p.tw, tid); __syncthreads();
-        // spectral product, fold onto 1024 points, conjugate (the inverse transform is conj(DFT(conj .)))
-        for (int k = tid; k < 1024; k += kD64Threads) {
-            const double2 w0 = dmul(b0[ph64(k)], __ldg(p.H + k)), w1 = dmul(b0[ph64(k + 1024)], __ldg(p.H + k + 1024));
-            b1[ph64(k)] = make_double2(w0.x + w1.x, -(w0.y + w1.y));
+        // ---- pass C (radix 8, Ns = 256): butterflies j = t and t + 128; outputs Z[j + 256 r] stay in registers, then the spectral
+        //      product and the fold W[k] + W[k + 1024] (keeps every other output sample): Yd[j + 256 r'], r' < 4, conjugated for
+        //      the inverse transform (IDFT = conj(DFT(conj .)))
+        double2 y[8];                                  // y[s] = conj(Yd[t + 128 s])
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = t + 128 * hh;
+            double2 z[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) z[r] = buf[pf64(j + 256 * r)];
+#pragma unroll
+            for (int r = 1; r < 8; ++r) z[r] = dmul(z[r], __ldg(p.tw + kTw64C + (r - 1) * 256 + j));
+            dft_regs<8>(z);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const double2 w0 = dmul(z[brev<8>(rr)], __ldg(p.H + j + 256 * rr));
+                const double2 w1 = dmul(z[brev<8>(rr + 4)], __ldg(p.H + j + 256 * (rr + 4)));
+                y[2 * rr + hh] = make_double2(w0.x + w1.x, -(w0.y + w1.y));
+            }
+        }
+        // ---- inverse 1024, pass D (radix 8, Ns = 1) on the registers
+        dft_regs<8>(y);
+        __syncthreads();                               // pass C's reads of the buffer are done
+#pragma unroll
+        for (int s = 0; s < 8; ++s) buf[pi64(8 * t + s)] = y[brev<8>(s)];
+        __syncthreads();
+        // ---- pass E (radix 8, Ns = 8)
+        {
+            const int k = t & 7;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) y[s] = buf[pi64(t + 128 * s)];
+#pragma unroll
+            for (int s = 1; s < 8; ++s) y[s] = dmul(y[s], __ldg(p.tw + kTw64E + (s - 1) * 8 + k));
+            dft_regs<8>(y);
+            __syncthreads();
+            const int j0 = (t - k) * 8 + k;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) buf[pi64(j0 + 8 * s)] = y[brev<8>(s)];
         }
         __syncthreads();
-        stockham_pass<1024, 4, 1>(b1, b0, p.tw, tid);    __syncthreads();
-        stockham_pass<1024, 4, 4>(b0, b1, p.tw, tid);    __syncthreads();
-        stockham_pass<1024, 4, 16>(b1, b0, p.tw, tid);   __syncthreads();
-        stockham_pass<1024, 4, 64>(b0, b1, p.tw, tid);   __syncthreads();
-        stockham_pass<1024, 4, 256>(b1, b0, p.tw, tid);  __syncthreads();
-        // b0[j] = conj(ydA[j] + i ydB[j]); output m = m0 + j - D for j >= D
-        for (int j = p.D + tid; j < 1024; j += kD64Threads) {
-            const double2 r = b0[ph64(j)];
-            const long long ma = mA + j - p.D, mb = mB + j - p.D;
-            if (ma < len_out) dst[ma] = (float)r.x;
-            if (haveB && mb < len_out) dst[mb] = (float)(-r.y);
+        // ---- pass F (radix 16, Ns = 64): 64 butterflies; output n = t + 64 r is conj(ydA[n] + i ydB[n]), stored for n >= D
+        if (t < 64) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = buf[pi64(t + 64 * r)];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) v[r] = dmul(v[r], __ldg(p.tw + kTw64F + (r - 1) * 64 + t));
+            dft_regs<16>(v);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int n = t + 64 * r;
+                if (n >= p.D) {
+                    const double2 o = v[brev<16>(r)];
+                    const long long ma = mA + n - p.D, mb = mB + n - p.D;
+                    if (ma < len_out) dst[ma] = (float)o.x;
+                    if (haveB && mb < len_out) dst[mb] = (float)(-o.y);
+                }
+            }
         }
     }
 }
@@ -2148,8 +2220,8 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 dp.tw = reinterpret_cast<const double2 *>(p.d_decim_tw64); dp.H = reinterpret_cast<const double2 *>(p.d_decim_h64);
                 dp.level_out = l; dp.D = D; dp.M = 1024 - D;
                 const int64_t npairs = (len + 2 * dp.M - 1) / (2 * dp.M);
-                dp.pairs_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs * batch / (148 * 3 * 2)));
-                const size_t fsmem = (size_t)(2 * kD64Buf) * sizeof(double2);
+                dp.pairs_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(8, npairs * batch / (148 * 4 * 2)));
+                const size_t fsmem = (size_t)kD64Buf * sizeof(double2);
                 dim3 grid((unsigned)((npairs + dp.pairs_per_cta - 1) / dp.pairs_per_cta), batch);
                 ProfScope ps(p, "decimate_fft64_kernel", lst);
                 decimate_fft64_kernel<<<grid, kD64Threads, fsmem, lst>>>(dp);
