@@ -14,6 +14,6 @@ from .features import (FeatureCombo, FeatureModule, CQT, HCQT, HVQT, MelSpec, Si
                        WaveformWrapper, framify_activations)
 from .stream import AudioStream, FeatureStream
 from . import ingest
-from .ingest import load_normalize_audio, resample, rms_norm, to_mono
+from .ingest import load_normalize_audio, pcm16_to_float, resample, rms_norm, to_mono
 
 __version__ = '0.1.0'

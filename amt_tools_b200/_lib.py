@@ -73,6 +73,7 @@ def _load():
         'amtfeat_resampler_table': (C.c_int64, [P, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         'amtfeat_ingest_workspace_bytes': (C.c_size_t, [C.c_int]),
         'amtfeat_resample': (C.c_int, [P, P, i64p, i64p, C.c_int, P, i64p, P, C.c_size_t, P]),
+        'amtfeat_pcm16_to_float': (C.c_int, [P, C.c_int64, C.c_float, P, P]),
         'amtfeat_to_mono': (C.c_int, [P, C.c_int64, C.c_int, P, P]),
         'amtfeat_rms_norm': (C.c_int, [P, i64p, i64p, C.c_int, P, C.c_size_t, P]),
         'amtfeat_profile_enable': (C.c_int, [P, C.c_int]),

@@ -234,6 +234,30 @@ int resample_run(const Resampler &r, const float *d_in, const int64_t *in_off, c
     return AMTFEAT_OK;
 }
 
+// 16-bit PCM (what a WAV file holds) -> float32 on the device: x * scale (soundfile / librosa.load: scale = 1 / 32768; a caller
+// that normalises by a known RMS folds it in).  Halves the host-to-device bytes of a device-resident consumer.
+__global__ void __launch_bounds__(256) pcm16_kernel(const short *__restrict__ in, float *__restrict__ out, long long n, float scale) {
+    const long long n4 = n >> 2;
+    const short4 *in4 = reinterpret_cast<const short4 *>(in);
+    float4 *out4 = reinterpret_cast<float4 *>(out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const short4 v = __ldg(in4 + i);
+        out4[i] = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[(n4 << 2) + threadIdx.x] = in[(n4 << 2) + threadIdx.x] * scale;
+}
+
+int pcm16_run(const short *d_in, int64_t n, float scale, float *d_out, void *stream) {
+    if (n <= 0) return AMTFEAT_OK;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 7) || (reinterpret_cast<uintptr_t>(d_out) & 15)) {
+        set_error("pcm16 input must be 8-byte aligned and the float32 output 16-byte aligned");
+        return AMTFEAT_ERR_INVALID;
+    }
+    pcm16_kernel<<<grid_for(n / 4 + 1), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_in, d_out, n, scale);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
 int to_mono_run(const float *d_in, int64_t n, int channels, float *d_out, void *stream) {
     if (channels < 1) { set_error("channels must be >= 1"); return AMTFEAT_ERR_INVALID; }
     if (n <= 0) return AMTFEAT_OK;
@@ -325,6 +349,11 @@ int amtfeat_resample(const amtfeat_resampler *r, const float *d_in, const int64_
         amtfeat::set_error(std::string("exception: ") + e.what());
         return AMTFEAT_ERR_INVALID;
     }
+}
+
+int amtfeat_pcm16_to_float(const int16_t *d_pcm, int64_t num_samples, float scale, float *d_out, void *stream) {
+    if (num_samples > 0 && (!d_pcm || !d_out)) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    return amtfeat::pcm16_run(reinterpret_cast<const short *>(d_pcm), num_samples, scale, d_out, stream);
 }
 
 int amtfeat_to_mono(const float *d_in, int64_t num_samples, int channels, float *d_out, void *stream) {

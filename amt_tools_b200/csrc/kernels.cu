@@ -878,7 +878,7 @@ struct TailParams {
     float *ladder;
     const ClipMeta *meta;
     const double *taps;
-    int ntaps, factor, level_in, level_out, alt, head;   // head: the head piece [0, alt_hlen) instead of the tail piece [alt_first, len)
+    int ntaps, factor, level_in, level_out, alt;         // blockIdx.z = 1: the head piece [0, alt_hlen) instead of the tail piece [alt_first, len)
 };
 
 // A CTA produces kTailOut = 4 x kThreads consecutive outputs, four per thread (64 apart: conflict-free shared-memory reads that
@@ -892,9 +892,10 @@ constexpr int kTailPerThread = 4, kTailOut = kTailPerThread * kThreads;
 __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
     extern __shared__ __align__(16) float tsm[];
     const ClipMeta *cm = p.meta + blockIdx.y;
+    const bool head = blockIdx.z != 0;
     long long first, end;
     float *dst;
-    if (p.head) {
+    if (head) {
         // a head piece that is part of the tail piece (alt_hoff == alt_off: whole level stored) is produced by the tail pass
         if (cm->alt_hlen[p.alt][p.level_out] <= 0 || cm->alt_first[p.alt][p.level_out] == 0) return;
         first = 0;
@@ -915,7 +916,7 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         src = p.audio + cm->in_off;
         lo = 0;
         hi = cm->n;
-    } else if (p.head && cm->alt_first[p.alt][p.level_in] != 0) {
+    } else if (head && cm->alt_first[p.alt][p.level_in] != 0) {
         src = p.ladder + cm->alt_hoff[p.alt][p.level_in];
         lo = 0;
         hi = cm->alt_hlen[p.alt][p.level_in];
@@ -1935,7 +1936,7 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
             if (it.nfft != last || cls != last_cls) { ++k; last = it.nfft; last_cls = cls; }
         }
         for (auto &kv : sl) k += (kv.second + kSlideMaxItems - 1) / kSlideMaxItems;
-        for (const AltLadder &al : p.alts) { (void)al; k += 2 * p.n_oct; }   // head + tail piece of every level of an exact ladder
+        for (const AltLadder &al : p.alts) { (void)al; k += p.n_oct; }   // one launch per level of an exact ladder (head and tail pieces)
     } else {
         k += 1;
     }
@@ -2310,22 +2311,19 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 tp.audio = d_audio; tp.ladder = d_ladder; tp.meta = d_meta; tp.alt = (int)a; tp.level_out = l;
                 if (l == al.eds) { tp.taps = al.d_taps; tp.ntaps = (int)al.taps.size(); tp.factor = 1 << al.eds; tp.level_in = 0; }
                 else { tp.taps = p.d_taps64; tp.ntaps = (int)p.taps64.size(); tp.factor = 2; tp.level_in = l - 1; }
-                for (int head = 0; head < 2; ++head) {
-                    int count = 0;
-                    for (int b = 0; b < batch; ++b) {
-                        if (head) { if (metas[b].alt_first[a][l] != 0) count = std::max(count, metas[b].alt_hlen[a][l]); }
-                        else if (metas[b].alt_first[a][l] >= 0) count = std::max(count, metas[b].lvl_len[l] - metas[b].alt_first[a][l]);
-                    }
-                    if (count <= 0) continue;
-                    tp.head = head;
-                    dim3 grid((count + kTailOut - 1) / kTailOut, batch);
-                    const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
-                    const size_t tsmem = ((size_t)tp.factor * ((kTailOut + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
-                    if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
-                    ProfScope ps(p, "tail_decimate_kernel", lst);
-                    tail_decimate_kernel<<<grid, kThreads, tsmem, lst>>>(tp);
-                    AMT_CUDA(cudaGetLastError());
+                int count = 0;       // one launch: tail pieces (z = 0) and head pieces (z = 1) of all clips
+                for (int b = 0; b < batch; ++b) {
+                    if (metas[b].alt_first[a][l] > 0) count = std::max(count, metas[b].alt_hlen[a][l]);
+                    if (metas[b].alt_first[a][l] >= 0) count = std::max(count, metas[b].lvl_len[l] - metas[b].alt_first[a][l]);
                 }
+                if (count <= 0) continue;
+                dim3 grid((count + kTailOut - 1) / kTailOut, batch, 2);
+                const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
+                const size_t tsmem = ((size_t)tp.factor * ((kTailOut + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
+                if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
+                ProfScope ps(p, "tail_decimate_kernel", lst);
+                tail_decimate_kernel<<<grid, kThreads, tsmem, lst>>>(tp);
+                AMT_CUDA(cudaGetLastError());
             }
         }
         if (!p.alts.empty()) {

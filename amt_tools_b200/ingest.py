@@ -114,6 +114,23 @@ def resample(audio, orig_sr, target_sr, res_type='kaiser_best', device=None):
     return _RESAMPLERS[key](audio)
 
 
+def pcm16_to_float(pcm, scale=1.0 / 32768.0, device=None):
+    """
+    16-bit PCM samples (np.int16 array or torch.int16 tensor, any shape, host or device) -> float32 CUDA tensor, pcm * scale:
+    what soundfile / librosa.load (tools/io.py:78) do on the host, after an upload of half the bytes.
+    """
+    dev = _device(device)
+    t = pcm if isinstance(pcm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm, dtype=np.int16))
+    if t.dtype != torch.int16:
+        raise ValueError('pcm16_to_float expects int16 samples')
+    t = t.to(dev, non_blocking=True).contiguous()
+    out = torch.empty(t.shape, dtype=torch.float32, device=dev)
+    if t.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib.amtfeat_pcm16_to_float(t.data_ptr(), t.numel(), float(scale), out.data_ptr(), _stream(dev)))
+    return out
+
+
 def to_mono(audio, device=None):
     """librosa.to_mono: (channels, N) -> (N,), the mean over channels; mono input is passed through."""
     dev = _device(device)

@@ -193,6 +193,9 @@ AMTFEAT_API int64_t amtfeat_resampler_table(const amtfeat_resampler *r, double *
 AMTFEAT_API size_t amtfeat_ingest_workspace_bytes(int batch);
 AMTFEAT_API int amtfeat_resample(const amtfeat_resampler *r, const float *d_in, const int64_t *in_offsets, const int64_t *num_samples,
                                  int batch, float *d_out, const int64_t *out_offsets, void *d_ws, size_t ws_bytes, void *stream);
+/* 16-bit PCM -> float32 on the device, d_out[i] = d_pcm[i] * scale (librosa.load / soundfile scale: 1 / 32768; tools/io.py:78): a
+ * device-resident consumer uploads half the bytes.  d_pcm 8-byte aligned, d_out 16-byte aligned. */
+AMTFEAT_API int amtfeat_pcm16_to_float(const int16_t *d_pcm, int64_t num_samples, float scale, float *d_out, void *stream);
 /* d_in is (channels, num_samples) row-major; d_out receives the channel mean */
 AMTFEAT_API int amtfeat_to_mono(const float *d_in, int64_t num_samples, int channels, float *d_out, void *stream);
 /* in place: clip / sqrt(mean(clip^2)); an all-zero (or empty) clip is left unchanged */

@@ -127,3 +127,15 @@ def test_rms_norm_to_mono_and_full_ingest():
     assert feats.shape == (1, 229, 1 + y.numel() // 512)
     with pytest.raises(ValueError):
         ab.load_normalize_audio(stereo, 44100, norm=np.inf)
+
+
+@pytest.mark.gpu
+def test_pcm16_to_float_on_device():
+    rs = np.random.RandomState(5)
+    for n in (0, 1, 3, 4, 1001, 44100):
+        pcm = rs.randint(-32768, 32768, n).astype(np.int16)
+        got = ab.pcm16_to_float(pcm).cpu().numpy()
+        assert got.dtype == np.float32 and np.array_equal(got, pcm.astype(np.float32) / 32768.0)   # what soundfile / librosa.load return
+    pcm = rs.randint(-32768, 32768, (3, 501)).astype(np.int16)
+    got = ab.pcm16_to_float(torch.from_numpy(pcm).cuda(), scale=0.5).cpu().numpy()
+    assert got.shape == (3, 501) and np.array_equal(got, pcm.astype(np.float32) * 0.5)
