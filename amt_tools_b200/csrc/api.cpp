@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -192,6 +193,7 @@ struct amtfeat_pipeline {
     };
     std::vector<Slot> slots;
     int64_t next_ticket = 0;
+    bool fused_epilogue = true;   // dB epilogue fused into the download (AMTFEAT_PIPE_FUSED=0: in-place pass + copy)
 };
 
 #define PIPE_CUDA(call)                                                                   \
@@ -228,7 +230,13 @@ static int pipeline_init(amtfeat_pipeline *p) {
     PIPE_CUDA(guard.status);
     PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
     PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking));
-    PIPE_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    {
+        // the fused epilogue + download kernel must not queue behind the compute grids of the next batch: highest priority
+        int prio_lo = 0, prio_hi = 0;
+        PIPE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const char *env = std::getenv("AMTFEAT_PIPE_PRIO");
+        PIPE_CUDA(cudaStreamCreateWithPriority(&p->s_d2h, cudaStreamNonBlocking, (env && std::string(env) == "0") ? prio_lo : prio_hi));
+    }
     for (auto &s : p->slots) {
         PIPE_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_audio), (size_t)std::max<int64_t>(p->max_audio, 4) * sizeof(float)));
         PIPE_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_out), (size_t)std::max<int64_t>(p->max_out, 4) * sizeof(float)));
@@ -249,6 +257,10 @@ int amtfeat_pipeline_create(int device, int nslots, int64_t max_audio_elems, int
     if (!p) { amtfeat::set_error("out of memory"); return AMTFEAT_ERR_INVALID; }
     p->device = device; p->nslots = nslots; p->max_audio = max_audio_elems; p->max_out = max_out_elems; p->max_ws = max_workspace_bytes;
     p->slots.resize(nslots);
+    {
+        const char *env = std::getenv("AMTFEAT_PIPE_FUSED");
+        p->fused_epilogue = !(env && std::string(env) == "0");
+    }
     const int rc = pipeline_init(p);
     if (rc != AMTFEAT_OK) { amtfeat_pipeline_destroy(p); return rc; }
     *out = p;
@@ -273,12 +285,28 @@ int amtfeat_pipeline_submit(amtfeat_pipeline *pipe, const amtfeat_plan *plan, co
     // compute: after the upload, and after the previous download of this slot's output
     PIPE_CUDA(cudaStreamWaitEvent(pipe->s_compute, s.uploaded, 0));
     PIPE_CUDA(cudaStreamWaitEvent(pipe->s_compute, s.downloaded, 0));
-    const int rc = amtfeat_process(plan, s.d_audio, in_offsets, num_samples, out_offsets, batch, s.d_out, s.d_ws, pipe->max_ws, pipe->s_compute);
+    // dB features: the (x - max) / 80 + 1 pass is fused into the download -- one kernel on the download stream reads the raw log
+    // values from HBM once and stores the finished features straight into the caller's pinned (mapped) host buffer, instead of an
+    // in-place pass over HBM followed by a copy.  AMTFEAT_PIPE_FUSED=0 keeps the two-step form (A/B).
+    const bool fused = pipe->fused_epilogue && amtfeat::has_db_epilogue(plan->p);
+    int rc, maxT = 0;
+    try {
+        rc = amtfeat::process(plan->p, s.d_audio, in_offsets, num_samples, out_offsets, batch, s.d_out, s.d_ws, pipe->max_ws, pipe->s_compute,
+                              fused, &maxT);
+    } catch (const std::exception &e) {
+        amtfeat::set_error(std::string("exception: ") + e.what());
+        rc = AMTFEAT_ERR_INVALID;
+    }
     if (rc != AMTFEAT_OK) return rc;
     PIPE_CUDA(cudaEventRecord(s.computed, pipe->s_compute));
     // download
     PIPE_CUDA(cudaStreamWaitEvent(pipe->s_d2h, s.computed, 0));
-    PIPE_CUDA(cudaMemcpyAsync(h_out, s.d_out, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_d2h));
+    if (fused) {
+        rc = amtfeat::epilogue_out(plan->p, s.d_out, s.d_ws, batch, maxT, h_out, true, pipe->s_d2h);
+        if (rc != AMTFEAT_OK) return rc;
+    } else {
+        PIPE_CUDA(cudaMemcpyAsync(h_out, s.d_out, (size_t)out_elems * sizeof(float), cudaMemcpyDeviceToHost, pipe->s_d2h));
+    }
     PIPE_CUDA(cudaEventRecord(s.downloaded, pipe->s_d2h));
     s.ticket = pipe->next_ticket;
     if (ticket) *ticket = pipe->next_ticket;

@@ -799,6 +799,10 @@ static int build_vqt(Plan &p) {
 }
 
 int build_plan_tables(Plan &p) {
+    {
+        const char *env_m = std::getenv("AMTFEAT_META_MEMCPY");
+        p.meta_memcpy = env_m && std::string(env_m) == "1";
+    }
     amtfeat_config &c = p.cfg;
     if (c.hop_length <= 0) { set_error("hop_length must be a positive integer"); return AMTFEAT_ERR_INVALID; }
     if (!(c.sample_rate > 0)) { set_error("sample_rate must be positive"); return AMTFEAT_ERR_INVALID; }

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -431,20 +432,24 @@ __device__ __forceinline__ float db_finish(float v, float ref_db, int scale01) {
     return scale01 ? v / 80.0f + 1.0f : v;
 }
 
-__global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict__ out, const ClipMeta *__restrict__ meta,
+// `dst` == `src`: in place (device-resident consumers).  `dst` = mapped pinned host memory (amtfeat_pipeline_*, same element offsets):
+// the features are read from HBM once and leave for the host in the same pass -- no second pass over HBM and no separate copy.
+__global__ void __launch_bounds__(kThreads) db_epilogue_kernel(const float *src, float *dst, const ClipMeta *__restrict__ meta,
                                                                 const float *__restrict__ maxbuf, int C, int F, int scale01) {
     const int seg = blockIdx.y, b = seg / C, c = seg % C;
     const ClipMeta *cm = meta + b;
     const long long count = (long long)F * cm->T;
-    float *o = out + cm->out_off + (long long)c * count;
+    const float *in = src + cm->out_off + (long long)c * count;
+    float *o = dst + cm->out_off + (long long)c * count;
     const float ref_db = db10(fmaxf(1e-10f, maxbuf[seg]));
-    // scalar head up to 16-byte alignment, float4 body, scalar tail
+    // scalar head up to 16-byte alignment, float4 body, scalar tail (src and dst share the element offset, hence the alignment)
     const long long head = min(count, (long long)(((16 - (reinterpret_cast<uintptr_t>(o) & 15)) & 15) >> 2));
     const long long nvec = (count - head) >> 2;
     const long long tail0 = head + (nvec << 2);
+    const float4 *i4 = reinterpret_cast<const float4 *>(in + head);
     float4 *o4 = reinterpret_cast<float4 *>(o + head);
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-        float4 v = o4[i];
+        float4 v = i4[i];
         v.x = db_finish(v.x, ref_db, scale01);
         v.y = db_finish(v.y, ref_db, scale01);
         v.z = db_finish(v.z, ref_db, scale01);
@@ -452,8 +457,8 @@ __global__ void __launch_bounds__(kThreads) db_epilogue_kernel(float *__restrict
         o4[i] = v;
     }
     if (blockIdx.x == 0) {
-        if (threadIdx.x < head) o[threadIdx.x] = db_finish(o[threadIdx.x], ref_db, scale01);
-        if (tail0 + threadIdx.x < count) o[tail0 + threadIdx.x] = db_finish(o[tail0 + threadIdx.x], ref_db, scale01);
+        if (threadIdx.x < head) o[threadIdx.x] = db_finish(in[threadIdx.x], ref_db, scale01);
+        if (tail0 + threadIdx.x < count) o[tail0 + threadIdx.x] = db_finish(in[tail0 + threadIdx.x], ref_db, scale01);
     }
 }
 
@@ -1650,6 +1655,13 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
 
+// Per-call clip descriptors: pinned host ring slot -> workspace, read over the bus by one small CTA.  A kernel, not a
+// cudaMemcpyAsync: a copy would queue on the host-to-device copy engine BEHIND the caller's bulk audio upload of the next
+// batch (measured: the device-consumer loop ran at upload + compute instead of max(upload, compute)).
+__global__ void __launch_bounds__(kThreads) copy_meta_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, int n16) {
+    for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // host: upload, workspace layout, launch
 // ------------------------------------------------------------------------------------------------
@@ -1829,6 +1841,7 @@ struct ProfScope {
 };
 
 static bool is_vqt_kind(const Plan &p) { return p.cfg.kind == AMTFEAT_VQT || p.cfg.kind == AMTFEAT_HVQT; }
+bool has_db_epilogue(const Plan &p) { return p.cfg.decibels && p.cfg.kind != AMTFEAT_WAVEFORM; }
 
 // Frames of one clip: T stored, T_all computed (the dB maximum of a harmonic runs over its own, untrimmed VQT: hvqt.py:123-128
 // converts every harmonic to dB before trimming it to the common frame count).
@@ -2088,8 +2101,32 @@ struct SideJoin {
     }
 };
 
+// The dB epilogue of a batch whose producers ran with defer_epilogue, written to `dst` (same element offsets as d_out; mapped
+// pinned host memory for the pipelined executor) on `stream`.  A handful of CTAs: the store stream is PCIe-bound, and the SMs
+// are busy with the next batch.
+int epilogue_out(const Plan &p, const float *d_out, void *d_ws, int batch, int maxT, float *dst, bool few_ctas, void *stream) {
+    if (!has_db_epilogue(p) || batch <= 0 || maxT <= 0) return AMTFEAT_OK;
+    DeviceGuard guard(p.device);
+    char *ws = static_cast<char *>(d_ws);
+    const ClipMeta *d_meta = reinterpret_cast<const ClipMeta *>(ws);
+    const float *d_max = reinterpret_cast<const float *>(ws + align_up((size_t)batch * sizeof(ClipMeta), 256));
+    const int64_t maxcount = (int64_t)p.F * maxT;
+    unsigned gx = (unsigned)std::min<int64_t>(1024, (maxcount + kThreads * 4 - 1) / (kThreads * 4));
+    if (few_ctas) {
+        static const int total = [] { const char *e = std::getenv("AMTFEAT_PIPE_CTAS"); return e ? std::max(1, atoi(e)) : 2 * 148; }();
+        gx = std::min<unsigned>(gx, std::max(1, (total + batch * p.C - 1) / (batch * p.C)));
+    }
+    dim3 grid(std::max(1u, gx), batch * p.C);
+    std::lock_guard<std::mutex> lock(p.call_mu);
+    ProfScope ps(p, few_ctas ? "db_epilogue_to_host_kernel" : "db_epilogue_kernel", reinterpret_cast<cudaStream_t>(stream));
+    db_epilogue_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_out, dst, d_meta, d_max, p.C, p.F,
+                                                                                        p.cfg.kind == AMTFEAT_POWER ? 0 : 1);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
-            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream) {
+            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream, bool defer_epilogue, int *max_frames) {
     if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
     if (batch <= 0) return AMTFEAT_OK;
     if ((reinterpret_cast<uintptr_t>(d_audio) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) || (reinterpret_cast<uintptr_t>(d_ws) & 255)) {
@@ -2116,6 +2153,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         maxTall = std::max<int>(maxTall, metas[b].T_all);
         maxn = std::max(maxn, n[b]);
     }
+    if (max_frames) *max_frames = maxT;
     if (maxT == 0) return AMTFEAT_OK;
     char *ws = static_cast<char *>(d_ws);
     ClipMeta *d_meta = reinterpret_cast<ClipMeta *>(ws + w.meta_off);
@@ -2144,7 +2182,14 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         AMT_CUDA(cudaEventSynchronize(ev));
         char *h = p.meta_ring + (size_t)slot * p.meta_slot_bytes;
         std::memcpy(h, metas.data(), need);
-        AMT_CUDA(cudaMemcpyAsync(d_meta, h, need, cudaMemcpyHostToDevice, st));
+        static_assert(sizeof(ClipMeta) % 16 == 0, "ClipMeta is copied in 16-byte words");
+        if (p.meta_memcpy) {
+            AMT_CUDA(cudaMemcpyAsync(d_meta, h, need, cudaMemcpyHostToDevice, st));
+        } else {
+            // pinned memory is device-addressable at its host address (unified addressing)
+            copy_meta_kernel<<<1, kThreads, 0, st>>>(reinterpret_cast<const int4 *>(h), reinterpret_cast<int4 *>(d_meta), (int)(need / 16));
+            AMT_CUDA(cudaGetLastError());
+        }
         AMT_CUDA(cudaEventRecord(ev, st));
     }
     if (c.decibels) AMT_CUDA(cudaMemsetAsync(d_max, 0, (size_t)batch * p.C * sizeof(float), st));
@@ -2337,12 +2382,12 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         }
         // `join` (destructor) gives the caller's stream a dependency on everything the side stream was given
     }
-    if (c.decibels) {
+    if (c.decibels && !defer_epilogue) {
         int64_t maxcount = (int64_t)p.F * maxT;
         unsigned gx = (unsigned)std::min<int64_t>(1024, (maxcount + kThreads * 4 - 1) / (kThreads * 4));
         dim3 grid(std::max(1u, gx), batch * p.C);
         ProfScope ps(p, "db_epilogue_kernel", st);
-        db_epilogue_kernel<<<grid, kThreads, 0, st>>>(d_out, d_meta, d_max, p.C, p.F, scale01);
+        db_epilogue_kernel<<<grid, kThreads, 0, st>>>(d_out, d_out, d_meta, d_max, p.C, p.F, scale01);
         AMT_CUDA(cudaGetLastError());
     }
     return AMTFEAT_OK;

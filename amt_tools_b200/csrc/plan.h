@@ -149,6 +149,7 @@ struct Plan {
     std::vector<double> decim_tw64;            // exp(-2 pi i m / 2048), m < 1024 (re, im)
     int decim_mode = 0;                        // 0: float64 fast convolution (default); AMTFEAT_DECIM=fft32 -> 1, =direct -> 2 (float32 forms, A/B)
     bool serial_launch = false;                // AMTFEAT_SERIAL=1: no side stream, every launch in order on the caller's stream (isolated per-kernel timing)
+    bool meta_memcpy = false;                  // AMTFEAT_META_MEMCPY=1: clip descriptors by cudaMemcpyAsync instead of copy_meta_kernel (A/B)
     bool slide_off = false;                    // AMTFEAT_SLIDE=0 keeps every item on the FFT-per-frame kernel (tests / A-B)
     std::vector<CqtRow> rows;                  // per-row description (host only; tests / describe)
     std::vector<cfloat> weights;               // per-row weights (host only)
@@ -230,6 +231,8 @@ int profile_read(const Plan &p, std::string &json);
 int framify(const float *d_in, long long rows, long long T, int win, int hop, long long lpad, long long hops, float *d_out,
             void *stream);
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
-            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream);
+            int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream, bool defer_epilogue = false, int *max_frames = nullptr);
+bool has_db_epilogue(const Plan &p);
+int epilogue_out(const Plan &p, const float *d_out, void *d_ws, int batch, int maxT, float *dst, bool few_ctas, void *stream);
 
 }  // namespace amtfeat

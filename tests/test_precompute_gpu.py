@@ -55,12 +55,17 @@ def test_device_framify_matches_reference_restated():
         assert got.shape == want.shape and np.array_equal(got, want)
 
 
-def test_pipeline_executor_matches_direct_calls():
-    """amtfeat_pipeline_* (upload / compute / download streams over staging slots) returns bit-identical features."""
+@pytest.mark.parametrize('fused', ['1', '0'])
+def test_pipeline_executor_matches_direct_calls(fused, monkeypatch):
+    """amtfeat_pipeline_* (upload / compute / download streams over staging slots) returns bit-identical features, with the dB
+    epilogue fused into the download (default: one kernel stores the finished features straight into the pinned host buffer) and
+    with the in-place pass + copy (AMTFEAT_PIPE_FUSED=0); linear features (no epilogue) go through the copy engine either way."""
+    monkeypatch.setenv('AMTFEAT_PIPE_FUSED', fused)
     import ctypes as C
     from amt_tools_b200 import _lib
-    mods = [ab.MelSpec(16000), ab.HCQT(22050, 256, n_bins=120, bins_per_octave=24, harmonics=[0.5, 1, 2, 3])]
-    srs = [16000, 22050]
+    mods = [ab.MelSpec(16000), ab.HCQT(22050, 256, n_bins=120, bins_per_octave=24, harmonics=[0.5, 1, 2, 3]),
+            ab.STFT(16000, decibels=False), ab.SignalPower(22050)]
+    srs = [16000, 22050, 16000, 22050]
     B = 3
     jobs = []
     for rep in range(5):            # more submissions than slots: buffers are recycled
