@@ -47,6 +47,12 @@
 #ifndef AMT_SLIDE_TILE
 #define AMT_SLIDE_TILE 4096    // samples of the level signal a sliding-DFT tile advances over (at most 1024 frames)
 #endif
+#ifndef AMT_CQT_MINB
+#define AMT_CQT_MINB 2         // resident CTAs per SM the FFT-per-frame kernels are compiled for (3 caps them at 80 registers: measured slower, profiles/)
+#endif
+#ifndef AMT_STFT_MINB
+#define AMT_STFT_MINB 2
+#endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
 #endif
@@ -221,7 +227,7 @@ __device__ __forceinline__ float store_tile(int rows, float *__restrict__ out, i
 }
 
 template <int NC, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) stft_kernel(const StftParams p) {
+__global__ void __launch_bounds__(kThreads, AMT_STFT_MINB) stft_kernel(const StftParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, PT = TT + 1, NFFT = 2 * NC;
     extern __shared__ __align__(16) float smem[];
@@ -1163,7 +1169,7 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
 //          each D value feeds 4 complex MACs.  Results go through a staging tile (also inside the retired scratch) so
 //          that the global stores are T-contiguous (16-byte vectors when the clip's rows are 16-byte aligned).
 template <int NC, bool HALF>
-__global__ void __launch_bounds__(kThreads, 2) cqt_kernel(const CqtParams p) {
+__global__ void __launch_bounds__(kThreads, AMT_CQT_MINB) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2, NFFT = 2 * NC;
     constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
@@ -1971,6 +1977,10 @@ static int launch_stft(const Plan &p, const StftParams &sp_in, int batch, int ma
     const int ntiles = (maxT + TT - 1) / TT;
     const long long total_tiles = (long long)ntiles * batch;
     sp.tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, total_tiles / (148 * 2 * 4)));
+    {
+        static const int forced = [] { const char *e = std::getenv("AMTFEAT_STFT_TPC"); return e ? atoi(e) : 0; }();
+        if (forced > 0) sp.tiles_per_cta = forced;
+    }
     dim3 grid((ntiles + sp.tiles_per_cta - 1) / sp.tiles_per_cta, batch);
     ProfScope ps(p, mel ? "stft_kernel_mel" : "stft_kernel_mag", st);
     if (mel) stft_kernel<NC, MODE_MEL><<<grid, kThreads, smem, st>>>(sp);

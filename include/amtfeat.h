@@ -12,8 +12,11 @@
  *   - every function returns an int status (0 = AMTFEAT_OK) unless it returns a value that cannot
  *     fail; on failure amtfeat_last_error() (thread-local) holds a message.  Nothing throws across
  *     the ABI, nothing calls exit().
- *   - a plan is immutable after creation: amtfeat_process* is re-entrant on distinct
- *     (stream, workspace) pairs.  The caller owns audio, output and workspace buffers.
+ *   - a plan's tables are immutable after creation: amtfeat_process* may be called concurrently on
+ *     distinct (stream, workspace) pairs; the calls serialise only their short host-side enqueue on
+ *     a plan lock (the clip-descriptor ring, the fork / join events of a call slot and the profiling
+ *     records of amtfeat_profile_* are plan state under that lock).  The caller owns audio, output
+ *     and workspace buffers.
  *   - device = -1 builds a host-only plan (all integer / time queries work, no GPU needed);
  *     amtfeat_process* on such a plan fails with AMTFEAT_ERR_NO_DEVICE.  There is no CPU compute path.
  */
