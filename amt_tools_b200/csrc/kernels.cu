@@ -1343,13 +1343,19 @@ __global__ void __launch_bounds__(kThreads, AMT_CQT_MINB) cqt_kernel(const CqtPa
 
 constexpr int kSlideMaxItems = 24;          // items per launch (grid.z)
 #ifndef AMT_SLIDE_FL
-#define AMT_SLIDE_FL 32
+#define AMT_SLIDE_FL 32        // frames per projection chunk
+#endif
+#ifndef AMT_SLIDE_BUFS
+#define AMT_SLIDE_BUFS 1       // Dbuf copies: 2 = chunks alternate between two buffers and need ONE barrier each instead of two.  Measured
+                               // (c5): 16-frame chunks x 2 copies (same shared memory) 1.31 ms against 1.19 ms -- the shorter projection
+                               // chunks cost more than the barrier saves; 32-frame chunks x 2 copies no longer fit two CTAs per SM
 #endif
 #ifndef AMT_SLIDE_CTAS
 #define AMT_SLIDE_CTAS 2
 #endif
 constexpr int kSlideFL = AMT_SLIDE_FL;      // frames per projection chunk
 constexpr int kSlideDP = kSlideFL + kDbufPad;   // Dbuf pitch (float2)
+constexpr int kSlideBufs = AMT_SLIDE_BUFS;
 
 struct SlideParams {
     const float *audio, *ladder;
@@ -1473,10 +1479,17 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     __syncthreads();
 
     float *out = p.out + cm->out_off;
-    for (int c0 = 0; c0 < Tt && t0 + c0 < tend; c0 += FL) {
+    // Chunks alternate between kSlideBufs copies of Dbuf (each kb x DP): with two, the sliding phase of chunk i + 1 writes the copy
+    // the projection of chunk i is NOT reading, so the only barrier a chunk needs is the one between its own two phases -- a
+    // thread passes it only after finishing the projection of the previous chunk, which orders that projection before the
+    // sliding phase (one chunk later) that overwrites its copy.  A slow warp of one phase is absorbed by the other.
+    const int buf_stride = kb * DP;
+    int chunk = 0;
+    for (int c0 = 0; c0 < Tt && t0 + c0 < tend; c0 += FL, ++chunk) {
         const unsigned skip = (t0 + c0 < sk_th || t0 + c0 >= sk_t0) ? p.alt_mask : 0u;
+        float2 *Dcur = Dbuf + (kSlideBufs > 1 ? (chunk & 1) * buf_stride : 0);
         if (active) {
-            float2 *dp = Dbuf + tid * DP;
+            float2 *dp = Dcur + tid * DP;
 #pragma unroll 4
             for (int f = 0; f < FL; ++f) {
                 if (!PD && (f & (RESEED - 1)) == 0) P = seed(t0 + c0 + f);
@@ -1492,11 +1505,11 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
             const bool vec2 = ((T & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
             for (int w = sub2; w < it.nblk; w += NT / LPB) {
                 const CqtBlock4 *bl = s_blk + w;
-                project_block2(bl, s_w + (bl->woff - it.woff0), Dbuf + (bl->col0 - it.kmin) * DP + 2 * lt2, DP, out, T, t0 + c0 + 2 * lt2,
+                project_block2(bl, s_w + (bl->woff - it.woff0), Dcur + (bl->col0 - it.kmin) * DP + 2 * lt2, DP, out, T, t0 + c0 + 2 * lt2,
                                p.decibels, s_max, gm2, LPB, lt2 == 0, vec2, skip, cm->t_max);
             }
         }
-        __syncthreads();
+        if (kSlideBufs == 1) __syncthreads();
     }
 }
 
@@ -1554,6 +1567,7 @@ __global__ void __launch_bounds__(kThreads, AMT_SLIDE_CTAS) cqt_slide_kernel(con
         case 2: slide_run<2>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
         default: slide_run<1>(p, it, tw2, cm, t0, tend, Tt, smem, s_max); break;
     }
+    __syncthreads();   // the last chunk's projection (its maxima in s_max) is complete
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
 
@@ -2085,7 +2099,7 @@ static int launch_slide(const Plan &p, const CqtParams &cp, const std::vector<in
         }
         if (tiles == 0) continue;
         const int threads = (maxkb + 31) / 32 * 32;
-        sp.w_off = (maxkb * kSlideDP * 2 + 3) / 4 * 4;
+        sp.w_off = (kSlideBufs * maxkb * kSlideDP * 2 + 3) / 4 * 4;
         sp.blk_off = sp.w_off + maxw * 4;
         sp.x_off = (sp.blk_off + maxblk * (int)(sizeof(CqtBlock4) / 4) + 3) / 4 * 4;
         const size_t smem = (size_t)(sp.x_off + maxx + 8) * sizeof(float);
