@@ -58,7 +58,7 @@ class Resampler(object):
                                                      -1 if host_only else self.device.index, C.byref(self.handle)))
 
     def __del__(self):
-        if getattr(self, 'handle', None):
+        if getattr(self, 'handle', None) and _lib is not None and getattr(_lib, 'lib', None) is not None:   # (module teardown)
             _lib.lib.amtfeat_resampler_destroy(self.handle)
             self.handle = None
 

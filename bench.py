@@ -779,6 +779,18 @@ def run_ours(args):
     # second pass over the output) next to the measured step: how far the FP32-bound kernels sit above it
     out_bytes = step_bytes - sum(4 * B * n for n in n_per)
     hbm_floor_ms = (step_bytes + 2 * out_bytes) / (hbm_peak * 1e9) * 1e3
+    # measured DRAM traffic of the whole step over its algorithmic bytes (in + out): producers from the ncu capture, plus the dB
+    # second pass -- 2 x out in place (device-resident consumers), 1 x out when it is fused into the download (pipelined executor)
+    try:
+        tfile = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+        prod = tfile['step_total_producers'][args.workload] * (B / float(tfile['traffic_bytes_per_launch']['captured_tracks_per_step'][args.workload]))
+        db_out = sum(4 * B * m.get_num_channels() * m.get_feature_size() * m.get_expected_frames(np.zeros(n, dtype=np.float32))
+                     for m, n in zip(mods, n_per) if getattr(m, 'decibels', False))
+        roofline['step_traffic_ratio'] = (prod + 2 * db_out) / step_bytes
+        roofline['e2e_traffic_ratio'] = (prod + db_out) / step_bytes
+        roofline['producers_traffic_ratio'] = prod / step_bytes
+    except Exception:
+        pass
     roofline['step_hbm_floor_ms'] = hbm_floor_ms
     roofline['step_frac_of_hbm_floor'] = hbm_floor_ms / (ms_total / args.steps)
     # the relevant compute roofline (every configuration is FP32-bound): algorithmic flops of the step over
@@ -805,7 +817,7 @@ def run_ours(args):
     launches = sum(int(_lib.lib.amtfeat_launch_count(m._dev_plan.handle, B, _lib.i64_array([n] * B)))
                    for m, n in zip(mods, n_per))
     flat = {'fp32_frac': roofline['fp32']['frac'], 'hbm_frac': roofline['frac'],
-            'step_traffic_ratio': roofline.get('step_traffic_ratio'),
+            'step_traffic_ratio': roofline.get('step_traffic_ratio'), 'e2e_traffic_ratio': roofline.get('e2e_traffic_ratio'),
             'e2e_device_value': (e2e or {}).get('device_consumer', {}).get('value') if e2e else None,
             'e2e_device_pcm16_value': (e2e or {}).get('device_consumer_pcm16', {}).get('value') if e2e else None,
             'e2e_d2h_ceiling_gbs': (e2e or {}).get('d2h_ceiling_GBps') if e2e else None,
