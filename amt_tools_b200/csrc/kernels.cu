@@ -53,6 +53,9 @@
 #ifndef AMT_STFT_MINB
 #define AMT_STFT_MINB 2
 #endif
+#ifndef AMT_TAIL_STREAM
+#define AMT_TAIL_STREAM 1      // exact-ladder pieces on their own side stream (0: behind the sliding-DFT launches on the ladder's stream)
+#endif
 #ifndef AMT_DBG_SKIP
 #define AMT_DBG_SKIP 0         // timing experiments only (results are wrong): 1 = no projection, 2 = no FFT, 3 = neither
 #endif
@@ -1742,6 +1745,9 @@ int upload_plan(Plan &p) {
             cudaStream_t side;
             AMT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_hi));
             p.side_stream[sl] = side;
+            cudaStream_t tail;
+            AMT_CUDA(cudaStreamCreateWithPriority(&tail, cudaStreamNonBlocking, prio_hi));
+            p.tail_stream[sl] = tail;
             for (void *&e : p.call_events[sl]) AMT_CUDA(cudaEventCreateWithFlags(reinterpret_cast<cudaEvent_t *>(&e), cudaEventDisableTiming));
         }
     }
@@ -1818,10 +1824,12 @@ void free_plan_device(Plan &p) {
     if (p.device < 0) return;
     DeviceGuard guard(p.device);
     for (int sl = 0; sl < Plan::kCallSlots; ++sl) {
-        if (p.side_stream[sl]) {
-            cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(p.side_stream[sl]));
-            cudaStreamDestroy(reinterpret_cast<cudaStream_t>(p.side_stream[sl]));
-            p.side_stream[sl] = nullptr;
+        for (void **sp : {&p.side_stream[sl], &p.tail_stream[sl]}) {
+            if (*sp) {
+                cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(*sp));
+                cudaStreamDestroy(reinterpret_cast<cudaStream_t>(*sp));
+                *sp = nullptr;
+            }
         }
         for (void *&e : p.call_events[sl])
             if (e) { cudaEventDestroy(reinterpret_cast<cudaEvent_t>(e)); e = nullptr; }
@@ -2119,7 +2127,7 @@ struct SideJoin {
     cudaEvent_t ev;
     bool armed = false;
     ~SideJoin() {
-        if (!armed) return;
+        if (!armed || side == st) return;
         cudaEventRecord(ev, side);
         cudaStreamWaitEvent(st, ev, 0);
     }
@@ -2276,11 +2284,19 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         for (const CqtItem &it : p.items)
             if (item_class(p, it, overlap) <= 2) max_fft_level = std::max(max_fft_level, (int)it.level);
         const int deep_level = std::min(p.n_levels - 1, std::max(max_fft_level, kMidLevel));
+        // the exact-ladder pieces and their items depend on the audio alone: their own stream, beside the shared ladder and the
+        // sliding-DFT launches (on short clips that chain was the critical path of the call)
+        cudaStream_t tst = (overlap && !p.alts.empty() && AMT_TAIL_STREAM) ? reinterpret_cast<cudaStream_t>(p.tail_stream[call_slot]) : lst;
         SideJoin join{st, lst, ev_side};
+        SideJoin join_tail{st, tst, reinterpret_cast<cudaEvent_t>(p.call_events[call_slot][4])};
         if (overlap) {
             AMT_CUDA(cudaEventRecord(ev_fork, st));        // clip descriptors / cleared maxima are in place
             AMT_CUDA(cudaStreamWaitEvent(lst, ev_fork, 0));
             join.armed = true;
+            if (tst != lst) {
+                AMT_CUDA(cudaStreamWaitEvent(tst, ev_fork, 0));
+                join_tail.armed = true;
+            }
         }
         for (int l = 1; l < p.n_levels; ++l) {
             len = (len + 1) / 2;
@@ -2337,7 +2353,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
         // class (narrow bands first: they hold the longest tiles), so that a narrow band does not carry the idle warps, registers
         // and shared memory of the widest one.  CTAs are handed out in grid order (z slowest): the items with the longest tiles
         // (smallest hop: most frames and the longest lead-in per tile) go first so that they do not form the tail of the launch.
-        auto launch_slides = [&](int cls) -> int {
+        auto launch_slides = [&](int cls, cudaStream_t s) -> int {
             std::map<int, std::vector<int>> classes;
             for (size_t i = 0; i < p.items.size(); ++i)
                 if (item_class(p, p.items[i], overlap) == cls) classes[slide_class(p.items[i])].push_back((int)i);
@@ -2346,7 +2362,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return p.items[a].hop < p.items[b].hop; });
                 std::vector<int> frames;
                 for (int i : idx) frames.push_back(cls == 5 ? tail_frames(p.items[i], slide_tile_frames(p.items[i].hop)) : maxTall);
-                const int r = launch_slide(p, cp, idx, frames, batch, cls == 5, lst);
+                const int r = launch_slide(p, cp, idx, frames, batch, cls == 5, s);
                 if (r) return r;
             }
             return AMTFEAT_OK;
@@ -2371,7 +2387,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             }
             return AMTFEAT_OK;
         };
-        if ((rc = launch_slides(3))) return rc;
+        if ((rc = launch_slides(3, lst))) return rc;
         // exact ladders: the tail of every level (level eds in one 2^eds : 1 pass over the audio), then their items
         for (size_t a = 0; a < p.alts.size(); ++a) {
             const AltLadder &al = p.alts[a];
@@ -2390,14 +2406,14 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
                 const size_t tsmem = ((size_t)tp.factor * ((kTailOut + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
                 if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
-                ProfScope ps(p, "tail_decimate_kernel", lst);
-                tail_decimate_kernel<<<grid, kThreads, tsmem, lst>>>(tp);
+                ProfScope ps(p, "tail_decimate_kernel", tst);
+                tail_decimate_kernel<<<grid, kThreads, tsmem, tst>>>(tp);
                 AMT_CUDA(cudaGetLastError());
             }
         }
         if (!p.alts.empty()) {
-            if ((rc = launch_ffts(4, lst))) return rc;
-            if ((rc = launch_slides(5))) return rc;
+            if ((rc = launch_ffts(4, tst))) return rc;
+            if ((rc = launch_slides(5, tst))) return rc;
         }
         for (int cls = 0; cls < (overlap ? 3 : 1); ++cls) {
             if (cls == 1) AMT_CUDA(cudaStreamWaitEvent(st, ev_mid, 0));

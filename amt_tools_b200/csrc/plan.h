@@ -190,7 +190,8 @@ struct Plan {
     // of call i; the host-side enqueue of a call is serialised per plan (call_mu), which makes reusing the events safe.
     static constexpr int kCallSlots = 2;
     void *side_stream[kCallSlots] = {};
-    void *call_events[kCallSlots][4] = {};
+    void *tail_stream[kCallSlots] = {};        // exact-ladder pieces (plans with alts): they read the audio only, so they run beside the shared ladder
+    void *call_events[kCallSlots][5] = {};     // fork, mid, all, side join, tail join
     mutable unsigned call_next = 0;
     mutable std::mutex call_mu;
 
