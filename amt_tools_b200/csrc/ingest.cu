@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -32,6 +33,16 @@ struct Resampler {
     int num_zeros = 0, num_table = 0, index_step = 0, nwin = 0;
     std::vector<double> win, delta;        // interp_win (already scaled by the ratio when downsampling), interp_delta
     double2 *d_tab = nullptr;              // (win, delta) pairs
+    // Phase-table form (integer sample rates: the fractional position repeats every q outputs, see resample_poly_kernel)
+    bool poly = false;
+    long long p = 0, q = 0;                // time_increment = sr_orig / sr_new = p / q in lowest terms
+    int Q = 0, P = 0;                      // super-period: Q = q m outputs <-> P = p m inputs (m makes Q >= 64)
+    int LT = 0, NTAP = 0;                  // taps of the left wing (x[n - LT + 1 .. n]) and in total, per phase, zero padded to the longest
+    int PADW = 0, WROW = 0;                // zero taps on either side of a weight row, row stride (PADW + NTAP + PADW)
+    int group = 0;                         // phases a warp accumulates together (1, 2 or 4); PB = 8 * group
+    int PB = 0, pitch = 0;                 // phases per pass of a CTA, row pitch (floats, odd) of its input tile
+    std::vector<double> W;                 // [q][WROW] float64 weights, win[offset + i step] + eta delta[offset + i step] per tap
+    double *d_W = nullptr;
 };
 
 static double bessel_i0_(double x) {
@@ -61,6 +72,70 @@ static void sinc_window(int num_zeros, int precision, double beta, double rollof
     }
 }
 
+constexpr int kPolyLanes = 32, kPolyWarps = 8;                    // super-periods per CTA (lanes), warps
+constexpr size_t kPolySmemMax = 110 * 1024, kPolyTableMax = 32u << 20;   // two CTAs per SM
+
+// Phase table of the polyphase form.  With integer sample rates time_register = t p / q, so output t uses
+//   n = floor(t p / q),  frac = (t p mod q) / q:  q distinct phases, each a fixed FIR over x[n - LT + 1 .. n + RT]
+// whose taps are exactly the weights the per-sample walk forms (left wing: offset = int(scale frac 2^prec), eta its fraction,
+// taps win[offset + i step] + eta delta[offset + i step], i < (nwin - offset) / step; right wing with scale - scale frac).
+// The walk's own truncation at the signal's ends (i <= n, n + 1 + k < n_in) equals zero extension of x.
+static void resampler_build_phases(Resampler &r) {
+    r.poly = false;
+    if (const char *e = std::getenv("AMTFEAT_RESAMPLE")) if (std::string(e) == "direct") return;
+    const double a = std::round(r.sr_orig), b = std::round(r.sr_new);
+    if (std::fabs(a - r.sr_orig) > 1e-9 || std::fabs(b - r.sr_new) > 1e-9 || a < 1 || b < 1 || a > 1e9 || b > 1e9) return;
+    long long x = (long long)a, y = (long long)b;
+    while (y) { const long long t = x % y; x = y; y = t; }
+    const long long p = (long long)a / x, q = (long long)b / x;
+    if (q > 2048) return;
+    const long long m = q >= 64 ? 1 : (64 + q - 1) / q;
+    if (p * m > (1 << 20)) return;
+    std::vector<std::vector<double>> wl((size_t)q), wr((size_t)q);
+    int LT = 0, RT = 0;
+    for (long long ph = 0; ph < q; ++ph) {
+        const double fracpos = (double)((ph * p) % q) / (double)q;
+        for (int wing = 0; wing < 2; ++wing) {
+            const double frac = wing == 0 ? r.scale * fracpos : r.scale - r.scale * fracpos;
+            const double index_frac = frac * r.num_table;
+            const int offset = (int)index_frac;
+            const double eta = index_frac - offset;
+            const int cnt = (r.nwin - offset) / r.index_step;
+            std::vector<double> &w = wing == 0 ? wl[(size_t)ph] : wr[(size_t)ph];
+            w.resize((size_t)std::max(cnt, 0));
+            for (int i = 0; i < cnt; ++i) w[(size_t)i] = r.win[(size_t)offset + (size_t)i * r.index_step] + eta * r.delta[(size_t)offset + (size_t)i * r.index_step];
+            (wing == 0 ? LT : RT) = std::max(wing == 0 ? LT : RT, cnt);
+        }
+    }
+    if (LT < 1) return;
+    const int NTAP = LT + RT;
+    // A CTA walks the phases in passes of PB = 8 warps x `group`: per pass it stages the input tile (32 super-periods, one row
+    // each) and the PB weight rows in shared memory.  A warp walks the input columns of its `group` consecutive phases together;
+    // phase u lags the first by n(a + u) - n(a) columns, which PADW zero taps on either side of every row absorb.
+    int group = 0, PADW = 0, WROW = 0, pitch = 0;
+    for (int cand = 4; cand >= 1; cand >>= 1) {
+        const int padw = (int)(((long long)(cand - 1) * p + q - 1) / q) + 1;
+        const int wrow = (padw + NTAP + padw + 1) & ~1;
+        const long long span = ((long long)kPolyWarps * cand * p + q - 1) / q + NTAP + 2;
+        const long long pt = span | 1;                                        // odd pitch: the lanes of a warp read one column of 32 rows
+        if ((size_t)kPolyLanes * pt * sizeof(float) + (size_t)kPolyWarps * cand * wrow * sizeof(double) <= kPolySmemMax) {
+            group = cand; PADW = padw; WROW = wrow; pitch = (int)pt;
+            break;
+        }
+    }
+    if (!group || (size_t)q * WROW * sizeof(double) > kPolyTableMax) return;
+    r.W.assign((size_t)q * WROW, 0.0);
+    for (long long ph = 0; ph < q; ++ph) {
+        double *row = r.W.data() + (size_t)ph * WROW + PADW;
+        for (int i = 0; i < (int)wl[(size_t)ph].size(); ++i) row[LT - 1 - i] = wl[(size_t)ph][(size_t)i];      // tap d reads x[n - (LT - 1) + d]
+        for (int k = 0; k < (int)wr[(size_t)ph].size(); ++k) row[LT + k] = wr[(size_t)ph][(size_t)k];
+    }
+    const int PB = kPolyWarps * group;
+    r.group = group;
+    r.p = p; r.q = q; r.Q = (int)(q * m); r.P = (int)(p * m); r.LT = LT; r.NTAP = NTAP; r.PADW = PADW; r.WROW = WROW; r.PB = PB; r.pitch = pitch;
+    r.poly = true;
+}
+
 int resampler_build(Resampler &r, double sr_orig, double sr_new, int filter) {
     if (!(sr_orig > 0) || !(sr_new > 0)) { set_error("sample rates must be positive"); return AMTFEAT_ERR_INVALID; }
     int precision = 9;
@@ -80,6 +155,7 @@ int resampler_build(Resampler &r, double sr_orig, double sr_new, int filter) {
     r.delta.back() = 0.0;                                                          // np.diff(..., append=interp_win[-1])
     r.index_step = (int)(r.scale * r.num_table);
     if (r.index_step < 1) { set_error("sample-rate ratio too small for the interpolation table"); return AMTFEAT_ERR_INVALID; }
+    resampler_build_phases(r);
     return AMTFEAT_OK;
 }
 
@@ -105,11 +181,21 @@ int resampler_upload(Resampler &r, int device) {
     for (size_t i = 0; i < tab.size(); ++i) tab[i] = make_double2(r.win[i], r.delta[i]);
     AMT_CUDA(cudaMalloc(reinterpret_cast<void **>(&r.d_tab), tab.size() * sizeof(double2)));
     AMT_CUDA(cudaMemcpy(r.d_tab, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    if (r.poly) {
+        AMT_CUDA(cudaMalloc(reinterpret_cast<void **>(&r.d_W), r.W.size() * sizeof(double)));
+        AMT_CUDA(cudaMemcpy(r.d_W, r.W.data(), r.W.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     return AMTFEAT_OK;
 }
 
 void resampler_free(Resampler &r) {
-    if (r.d_tab) { DeviceGuard guard(r.device); cudaFree(r.d_tab); r.d_tab = nullptr; }
+    if (r.d_tab || r.d_W) {
+        DeviceGuard guard(r.device);
+        if (r.d_tab) cudaFree(r.d_tab);
+        if (r.d_W) cudaFree(r.d_W);
+        r.d_tab = nullptr;
+        r.d_W = nullptr;
+    }
 }
 
 struct IngestClip {
@@ -156,6 +242,91 @@ __global__ void __launch_bounds__(256) resample_kernel(const float *__restrict__
             }
         }
         out[c.out_off + t] = (float)acc;
+    }
+}
+
+// Polyphase form of the same resampler (integer sample rates; resampler_build_phases).
+//   A CTA takes 32 consecutive super-periods of one clip -- lane g owns super-period gb + g, i.e. the outputs
+//   t = (gb + g) Q + a, a < Q -- and walks the phases a in passes of PB.  Per pass the inputs the 32 x PB outputs read are staged
+//   once in shared memory, one row per super-period with an ODD pitch: the lanes of a warp (same phase, hence the same,
+//   warp-uniform weights) read their rows at the same column, conflict free.  A warp accumulates kPolyGroup phases at once
+//   in ONE walk over their common input columns (every sample read and converted once, feeding all phases; independent
+//   float64 chains); weights are fetched as aligned pairs of taps from the phase's contiguous row.
+//   Every input sample is loaded from global memory once per pass, every weight row once per CTA.
+struct PolyParams {
+    const float *in;
+    float *out;
+    const IngestClip *clips;
+    const double *W;
+    long long p, q;
+    int Q, P, LT, NTAP, PADW, WROW, pitch;
+    double ratio;
+};
+
+template <int GROUP>
+__global__ void __launch_bounds__(kPolyWarps * 32) resample_poly_kernel(const PolyParams pp) {
+    constexpr int PB = kPolyWarps * GROUP;
+    extern __shared__ __align__(16) float tile[];
+    double *wsm = reinterpret_cast<double *>(tile + (size_t)kPolyLanes * pp.pitch + ((kPolyLanes * pp.pitch) & 1));   // [PB][WROW]
+    const IngestClip c = pp.clips[blockIdx.y];
+    const long long gb = (long long)blockIdx.x * kPolyLanes;
+    if (gb * pp.Q >= c.n_out) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *x = pp.in + c.in_off;
+    float *y = pp.out + c.out_off;
+    const long long n_res = (long long)((double)c.n_in * pp.ratio);       // samples resampy itself produces; the rest is fix_length's zero padding
+    const long long tbase = (gb + lane) * pp.Q;
+    for (int a0 = 0; a0 < pp.Q; a0 += PB) {
+        const int a1 = min(pp.Q, a0 + PB);
+        const long long n_lo = ((long long)a0 * pp.p) / pp.q, n_hi = ((long long)(a1 - 1) * pp.p) / pp.q;
+        const int lrow = (int)(n_hi - n_lo) + pp.NTAP + 1;
+        __syncthreads();                                                   // the previous pass is done with the tile and the weights
+        for (int r = warp; r < kPolyLanes; r += kPolyWarps) {
+            const long long j0 = (gb + r) * pp.P + n_lo - (pp.LT - 1);
+            float *row = tile + (size_t)r * pp.pitch;
+            for (int k = lane; k < lrow; k += 32) {
+                const long long j = j0 + k;
+                row[k] = (j >= 0 && j < c.n_in) ? __ldg(x + j) : 0.f;
+            }
+        }
+        for (int r = warp; r < PB; r += kPolyWarps) {                      // phases past the end repeat the last one (results dropped)
+            const double *src = pp.W + (size_t)(min(a0 + r, pp.Q - 1) % pp.q) * pp.WROW;
+            double *dst = wsm + (size_t)r * pp.WROW;
+            for (int k = lane; k < pp.WROW; k += 32) dst[k] = __ldg(src + k);
+        }
+        __syncthreads();
+        // one walk over the input columns of the warp's GROUP phases: every sample is read and converted ONCE and feeds all of
+        // them (phase u multiplies column col by its tap col - shift_u; the zero taps around a row make that unconditional);
+        // the weights are warp-uniform shared-memory reads (broadcast), the samples conflict free (odd pitch)
+        const int abase = a0 + warp * GROUP;
+        if (abase < a1) {
+            const double *wrow[GROUP];
+            double acc[GROUP];
+            const long long n_first = ((long long)abase * pp.p) / pp.q;
+            int shift_max = 0;
+#pragma unroll
+            for (int u = 0; u < GROUP; ++u) {
+                const int a = min(abase + u, a1 - 1);
+                const int shift = (int)(((long long)a * pp.p) / pp.q - n_first);
+                wrow[u] = wsm + (size_t)(warp * GROUP + min(u, a1 - 1 - abase)) * pp.WROW + pp.PADW - shift;
+                shift_max = max(shift_max, shift);
+                acc[u] = 0.0;
+            }
+            const float *xr = tile + (size_t)lane * pp.pitch + (int)(n_first - n_lo);
+            const int ncol = pp.NTAP + shift_max;
+#pragma unroll 4
+            for (int col = 0; col < ncol; ++col) {
+                const double xv = (double)xr[col];
+#pragma unroll
+                for (int u = 0; u < GROUP; ++u) acc[u] = fma(wrow[u][col], xv, acc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < GROUP; ++u) {
+                const int a = abase + u;
+                const long long t = tbase + a;
+                if (a < a1 && t < c.n_out) y[t] = t < n_res ? (float)acc[u] : 0.f;
+            }
+        }
     }
 }
 
@@ -228,6 +399,25 @@ int resample_run(const Resampler &r, const float *d_in, const int64_t *in_off, c
     IngestClip *d_clips; double *d_acc;
     int rc = stage_clips(in_off, n_in, out_off, n_out.data(), batch, d_ws, ws_bytes, st, &d_clips, &d_acc);
     if (rc) return rc;
+    if (r.poly) {
+        PolyParams pp{d_in, d_out, d_clips, r.d_W, r.p, r.q, r.Q, r.P, r.LT, r.NTAP, r.PADW, r.WROW, r.pitch, r.ratio};
+        const size_t tile_floats = (size_t)kPolyLanes * r.pitch + (((size_t)kPolyLanes * r.pitch) & 1);
+        const size_t smem = tile_floats * sizeof(float) + (size_t)kPolyWarps * r.group * r.WROW * sizeof(double);
+        static bool attr_set[64] = {};
+        if (r.device >= 0 && r.device < 64 && !attr_set[r.device]) {
+            AMT_CUDA(cudaFuncSetAttribute(resample_poly_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmemMax + 1024));
+            AMT_CUDA(cudaFuncSetAttribute(resample_poly_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmemMax + 1024));
+            AMT_CUDA(cudaFuncSetAttribute(resample_poly_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolySmemMax + 1024));
+            attr_set[r.device] = true;
+        }
+        const long long supers = (maxo + r.Q - 1) / r.Q;
+        dim3 grid((unsigned)((supers + kPolyLanes - 1) / kPolyLanes), batch);
+        if (r.group == 4) resample_poly_kernel<4><<<grid, kPolyWarps * 32, smem, st>>>(pp);
+        else if (r.group == 2) resample_poly_kernel<2><<<grid, kPolyWarps * 32, smem, st>>>(pp);
+        else resample_poly_kernel<1><<<grid, kPolyWarps * 32, smem, st>>>(pp);
+        AMT_CUDA(cudaGetLastError());
+        return AMTFEAT_OK;
+    }
     dim3 grid(grid_for(maxo), batch);
     resample_kernel<<<grid, 256, 0, st>>>(d_in, d_out, d_clips, r.d_tab, r.nwin, r.num_table, r.index_step, r.scale, 1.0 / r.ratio, r.ratio);
     AMT_CUDA(cudaGetLastError());

@@ -6,6 +6,8 @@ CPU tests pin the oracle restatement (oracle/ingest.py) with known answers and c
 length arithmetic against it; GPU tests compare the CUDA kernels with the oracle on the same seeded inputs.
 The resampler's parity is UNPINNED (resampy is not installable here): the known answers fix the scale chain only.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +16,8 @@ import amt_tools_b200 as ab
 from amt_tools_b200.ingest import Resampler
 from amt_tools_b200.synth import piano_like
 from oracle import ingest as oi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [(44100, 22050, 'kaiser_best'), (44100, 16000, 'kaiser_best'), (16000, 22050, 'kaiser_fast'),
          (48000, 22050, 'kaiser_fast'), (22050, 22050 * 2, 'kaiser_best')]
@@ -139,3 +143,31 @@ def test_pcm16_to_float_on_device():
     pcm = rs.randint(-32768, 32768, (3, 501)).astype(np.int16)
     got = ab.pcm16_to_float(torch.from_numpy(pcm).cuda(), scale=0.5).cpu().numpy()
     assert got.shape == (3, 501) and np.array_equal(got, pcm.astype(np.float32) * 0.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('a,b', [(44100, 22050), (44100, 16000), (48000, 22050), (22050, 44100), (16000, 22050), (32000, 16000), (96000, 16000)])
+def test_polyphase_resampler_equals_the_per_sample_walk(a, b):
+    """The phase-table kernel (integer sample rates) against the per-sample table walk it replaces (AMTFEAT_RESAMPLE=direct), both on
+    the device: same float64 weights, same zero extension, summation order aside."""
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import amt_tools_b200 as ab; from amt_tools_b200.synth import piano_like\n"
+            "x = piano_like(%d * 2 + 1237, %d, seed=4)\n"
+            "outs = ab.resample([x, x[:3001], x[:7]], %d, %d)\n"
+            "np.save(sys.argv[1], np.concatenate([o.cpu().numpy() for o in outs]))\n") % (ROOT, a, a, a, b)
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ('poly', 'direct'):
+            env = dict(os.environ)
+            if mode == 'direct':
+                env['AMTFEAT_RESAMPLE'] = 'direct'
+            else:
+                env.pop('AMTFEAT_RESAMPLE', None)
+            out = os.path.join(d, mode + '.npy')
+            subprocess.run([sys.executable, '-c', code, out], check=True, env=env)
+            res[mode] = np.load(out)
+    assert res['poly'].shape == res['direct'].shape
+    scale = max(np.abs(res['direct']).max(), 1e-30)
+    assert np.abs(res['poly'] - res['direct']).max() <= 2e-7 * scale     # float32 roundings of float64 sums that differ by ~1e-16
