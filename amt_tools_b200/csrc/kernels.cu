@@ -901,9 +901,11 @@ struct TailParams {
 // float32 (exact products of float32 data and float32-rounded taps, three additions) and folded into a float64 accumulator:
 // the result carries one float32 rounding per 4 taps of its 4-tap partial sums and none from the long summation -- as good as
 // the final rounding to float32 -- at a quarter of the float64 operations and shared-memory wavefronts of a plain float64 loop.
-constexpr int kTailPerThread = 4, kTailOut = kTailPerThread * kThreads;
-
+// PT = 4 outputs per thread amortises the tap loads; PT = 1 (four times the CTAs) when the pieces of a batch are too few to fill
+// the GPU otherwise (short clips: the launch is latency bound, one thread walking all taps of four outputs).
+template <int PT>
 __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
+    constexpr int kTailPerThread = PT, kTailOut = PT * kThreads;
     extern __shared__ __align__(16) float tsm[];
     const ClipMeta *cm = p.meta + blockIdx.y;
     const bool head = blockIdx.z != 0;
@@ -955,7 +957,9 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
         X[ph * JP + j] = (g >= lo && g < hi) ? src[g] : 0.f;
     }
     __syncthreads();
-    double acc[kTailPerThread] = {0.0, 0.0, 0.0, 0.0};
+    double acc[kTailPerThread];
+#pragma unroll
+    for (int r = 0; r < kTailPerThread; ++r) acc[r] = 0.0;
     for (int ph = 0; ph < F; ++ph) {
         const float *xp = X + ph * JP + threadIdx.x + nq - 1, *hp = hs + ph * nq;
         for (int q = 0; q < nq; q += 4) {
@@ -1759,7 +1763,8 @@ int upload_plan(Plan &p) {
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(cqt_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
@@ -2402,12 +2407,17 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                     if (metas[b].alt_first[a][l] >= 0) count = std::max(count, metas[b].lvl_len[l] - metas[b].alt_first[a][l]);
                 }
                 if (count <= 0) continue;
-                dim3 grid((count + kTailOut - 1) / kTailOut, batch, 2);
+                // four outputs per thread unless that leaves the GPU mostly empty (CTAs of a launch: pieces x clips x 2)
+                const int out4 = 4 * kThreads;
+                const bool wide = (long long)((count + out4 - 1) / out4) * batch * 2 >= 2 * 148;
+                const int tail_out = wide ? out4 : kThreads;
+                dim3 grid((count + tail_out - 1) / tail_out, batch, 2);
                 const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
-                const size_t tsmem = ((size_t)tp.factor * ((kTailOut + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
+                const size_t tsmem = ((size_t)tp.factor * ((tail_out + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
                 if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
                 ProfScope ps(p, "tail_decimate_kernel", tst);
-                tail_decimate_kernel<<<grid, kThreads, tsmem, tst>>>(tp);
+                if (wide) tail_decimate_kernel<4><<<grid, kThreads, tsmem, tst>>>(tp);
+                else tail_decimate_kernel<1><<<grid, kThreads, tsmem, tst>>>(tp);
                 AMT_CUDA(cudaGetLastError());
             }
         }
