@@ -1682,11 +1682,12 @@ __global__ void __launch_bounds__(kThreads, 2) cqt_small_kernel(const CqtParams 
     if (p.decibels && tid < p.C && s_max[tid] != 0) atomicMax(reinterpret_cast<int *>(p.maxbuf) + blockIdx.y * p.C + tid, s_max[tid]);
 }
 
-// Per-call clip descriptors: pinned host ring slot -> workspace, read over the bus by one small CTA.  A kernel, not a
+// Per-call clip descriptors: pinned host ring slot -> workspace, read over the bus by a few small CTAs.  A kernel, not a
 // cudaMemcpyAsync: a copy would queue on the host-to-device copy engine BEHIND the caller's bulk audio upload of the next
 // batch (measured: the device-consumer loop ran at upload + compute instead of max(upload, compute)).
 __global__ void __launch_bounds__(kThreads) copy_meta_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, int n16) {
-    for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = src[i];
+    const int i = blockIdx.x * kThreads + threadIdx.x;     // one 16-byte word per thread: every bus read of the copy is in flight at once
+    if (i < n16) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2224,7 +2225,8 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
             AMT_CUDA(cudaMemcpyAsync(d_meta, h, need, cudaMemcpyHostToDevice, st));
         } else {
             // pinned memory is device-addressable at its host address (unified addressing)
-            copy_meta_kernel<<<1, kThreads, 0, st>>>(reinterpret_cast<const int4 *>(h), reinterpret_cast<int4 *>(d_meta), (int)(need / 16));
+            const int n16 = (int)(need / 16);
+            copy_meta_kernel<<<(n16 + kThreads - 1) / kThreads, kThreads, 0, st>>>(reinterpret_cast<const int4 *>(h), reinterpret_cast<int4 *>(d_meta), n16);
             AMT_CUDA(cudaGetLastError());
         }
         AMT_CUDA(cudaEventRecord(ev, st));
