@@ -238,6 +238,29 @@ int sample_range(const Plan &p, int64_t frames, int64_t *lo, int64_t *hi) {
 // table design
 // ------------------------------------------------------------------------------------------------
 
+// numpy's pairwise summation of a contiguous float32 vector (umath loops_utils pairwise_sum: 8 accumulators on blocks of at
+// most 128, recursive halving above), so that np.sum(mags) is reproduced to the bit.
+static float np_pairwise_sum_f32(const float *a, size_t n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (size_t i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        size_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum_f32(a, n2) + np_pairwise_sum_f32(a + n2, n - n2);
+}
+
 static void fft_inplace(std::vector<std::complex<double>> &a) {  // forward DFT, radix-2, n power of two
     const size_t n = a.size();
     for (size_t i = 1, j = 0; i < n; ++i) {
@@ -652,20 +675,33 @@ static int build_vqt(Plan &p) {
                 }
                 fft_inplace(a);
                 const int nb = nfft / 2 + 1;
-                // sparsify_rows(quantile = 0.01)
-                std::vector<double> mags(nb);
-                double norm = 0;
+                // sparsify_rows(quantile = 0.01) in the arithmetic librosa runs it in: fft_basis is complex64, so np.abs, np.sum
+                // (pairwise), the division and np.cumsum (sequential) are all float32.  The threshold decision sits on a
+                // cumulative sum of ~1000 terms: for some rows the 0.01 crossing is decided by 1e-6 of its value, which float64
+                // arithmetic here would settle differently from the float32 the reference (and the oracle) uses.
+#ifdef AMT_SPARSIFY_F64
+                typedef double sp_t;
+#else
+                typedef float sp_t;
+#endif
+                std::vector<sp_t> mags(nb);
                 for (int q = 0; q < nb; ++q) {
                     a[q] = std::complex<double>((float)a[q].real(), (float)a[q].imag());
-                    mags[q] = std::abs(a[q]);
-                    norm += mags[q];
+                    mags[q] = sizeof(sp_t) == 4 ? (sp_t)hypotf((float)a[q].real(), (float)a[q].imag()) : (sp_t)std::abs(a[q]);
                 }
-                std::vector<double> srt(mags);
+                sp_t norm = 0;
+                if (sizeof(sp_t) == 4) {
+                    std::vector<float> mf(mags.begin(), mags.end());
+                    norm = (sp_t)np_pairwise_sum_f32(mf.data(), (size_t)nb);
+                } else {
+                    for (int q = 0; q < nb; ++q) norm += mags[q];
+                }
+                std::vector<sp_t> srt(mags);
                 std::sort(srt.begin(), srt.end());
-                double cum = 0, thr = srt.back();
+                sp_t cum = 0, thr = srt.back();
                 for (int q = 0; q < nb; ++q) {
                     cum += srt[q] / norm;
-                    if (!(cum < 0.01)) { thr = srt[q]; break; }
+                    if (!(cum < (sp_t)0.01)) { thr = srt[q]; break; }
                 }
                 int first = -1, last = -1;
                 for (int q = 0; q < nb; ++q)
@@ -831,6 +867,12 @@ int build_plan_tables(Plan &p) {
             } else {
                 p.F = c.n_fft / 2 + 1;
             }
+            // the kernel's shared-memory tiles depend on the configuration alone: reject what cannot run when the module is
+            // constructed (a ValueError there), not at the first process_audio call
+            if (stft_smem_bytes(p) > 227 * 1024) {
+                set_error("hop_length / n_mels too large for the shared-memory tiles of this n_fft");
+                return AMTFEAT_ERR_INVALID;
+            }
             return AMTFEAT_OK;
         case AMTFEAT_VQT:
         case AMTFEAT_HVQT:
@@ -870,6 +912,18 @@ std::string describe(const Plan &p) {
               << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << ", \"alt\": " << it.alt << "}";
         }
         o << "]";
+        if (const char *e = std::getenv("AMTFEAT_DESCRIBE_ROWS")) {
+            if (std::string(e) == "1") {     // per basis row: channel, bin, first kept FFT bin, band width, kept entries (tests / debugging)
+                o << ", \"rows\": [";
+                for (size_t r = 0; r < p.rows.size(); ++r) {
+                    const CqtRow &rw = p.rows[r];
+                    int nnz = 0;
+                    for (int q = 0; q < rw.cnt; ++q) nnz += (p.weights[rw.woff + q].x != 0.f || p.weights[rw.woff + q].y != 0.f);
+                    o << (r ? ", " : "") << "[" << rw.chan << ", " << rw.bin << ", " << rw.col0 << ", " << rw.cnt << ", " << nnz << "]";
+                }
+                o << "]";
+            }
+        }
     }
     o << "}";
     return o.str();

@@ -1991,6 +1991,26 @@ int launch_count(const Plan &p, int batch, const int64_t *n) {
     return k;
 }
 
+template <int NC> static size_t stft_smem_nc(const Plan &p) {
+    using L = FftLayout<NC>;
+    const int TT = kWarpsPerCta * L::G;
+    const size_t scr = stft_scr_floats<NC>(p.cfg.n_mels, p.cfg.kind == AMTFEAT_MEL);
+    return (size_t)(2 * NC + NC + scr + tile_floats_for(TT, p.cfg.hop_length, 2 * NC)) * sizeof(float);
+}
+size_t stft_smem_bytes(const Plan &p) {
+    switch (p.cfg.n_fft / 2) {
+        case 1024: return stft_smem_nc<1024>(p);
+        case 512: return stft_smem_nc<512>(p);
+        case 256: return stft_smem_nc<256>(p);
+        case 128: return stft_smem_nc<128>(p);
+        case 64: return stft_smem_nc<64>(p);
+        case 32: return stft_smem_nc<32>(p);
+        case 16: return stft_smem_nc<16>(p);
+        case 8: return stft_smem_nc<8>(p);
+        default: return stft_smem_nc<4>(p);
+    }
+}
+
 template <int NC>
 static int launch_stft(const Plan &p, const StftParams &sp_in, int batch, int maxT, cudaStream_t st) {
     using L = FftLayout<NC>;

@@ -234,6 +234,7 @@ int framify(const float *d_in, long long rows, long long T, int win, int hop, lo
 int process(const Plan &p, const float *d_audio, const int64_t *in_off, const int64_t *n, const int64_t *out_off,
             int batch, float *d_out, void *d_ws, size_t ws_bytes, void *stream, bool defer_epilogue = false, int *max_frames = nullptr);
 bool has_db_epilogue(const Plan &p);
+size_t stft_smem_bytes(const Plan &p);   // dynamic shared memory of stft_kernel for this (STFT / MEL) configuration
 int epilogue_out(const Plan &p, const float *d_out, void *d_ws, int batch, int maxT, float *dst, bool few_ctas, void *stream);
 
 }  // namespace amtfeat

@@ -169,3 +169,26 @@ def test_no_cpu_fallback():
     n = _lib.i64_array([4000])
     rc = _lib.lib.amtfeat_process(m._host_plan.handle, None, _lib.i64_array([0]), n, _lib.i64_array([0]), 1, None, None, 1 << 30, None)
     assert rc == _lib.ERR_NO_DEVICE
+
+
+def test_sparsified_basis_rows_match_the_oracle(monkeypatch):
+    """Kept set of every wavelet row (first kept FFT bin, band width, number of kept entries) of the C++ plan against the oracle's
+    `vqt_filter_fft` + `sparsify_rows` for the BASELINE CQT / VQT / HCQT configurations and a few others.  The 1 % threshold sits on a
+    float32 cumulative sum in librosa, so the plan runs that step in float32 as well (np.abs, pairwise np.sum, sequential np.cumsum).
+    (Rows whose threshold crossing is decided by less than the noise of the reference's own float32 FFT -- e.g. fmin 55, 60 bins per
+    octave, 299 bins at 22050 Hz, row 30 of every octave -- cannot be pinned by any restatement: DESIGN.md, "Known deviations".)"""
+    monkeypatch.setenv('AMTFEAT_DESCRIBE_ROWS', '1')
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('rows_vs_oracle', os.path.join(ROOT, 'tools', 'rows_vs_oracle.py'))
+    rv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rv)
+    cases = [(22050, 192, 24, rv.ls.NOTE_C1_HZ, 0.0, 512), (22050, 84, 12, rv.ls.NOTE_C1_HZ, 24.7 * (2 ** (1 / 12) - 1) / 0.108, 512),
+             (22050, 360, 60, rv.ls.NOTE_C1_HZ, 0.0, 256), (22050, 360, 60, rv.ls.NOTE_C1_HZ * 0.5, 0.0, 256), (22050, 360, 60, rv.ls.NOTE_C1_HZ * 3, 0.0, 256),
+             (44100, 96, 12, rv.ls.NOTE_C1_HZ, 5.0, 1024), (16000, 143, 36, 27.5, 25.0, 16)]
+    for sr, n_bins, bpo, fmin, gamma, hop in cases:
+        m = ab.VQT(sample_rate=sr, hop_length=hop, n_bins=n_bins, bins_per_octave=bpo, fmin=fmin, gamma=gamma)
+        d = m.describe()
+        want = rv.oracle_rows(sr, n_bins, bpo, fmin, gamma, d['eds_lib'][0])
+        assert len(d['rows']) >= n_bins
+        for chan, b, col0, cnt, nnz in d['rows']:
+            assert want[b] == (col0, cnt, nnz), (sr, n_bins, bpo, fmin, b, (col0, cnt, nnz), want[b])
