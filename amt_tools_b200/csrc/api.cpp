@@ -114,7 +114,7 @@ int amtfeat_out_shape(const amtfeat_plan *plan, int64_t n, int64_t shape[3], int
     const Plan &p = plan->p;
     const amtfeat_config &c = p.cfg;
     const int64_t T = amtfeat::output_frames(p, n);
-    if (T < 0) { amtfeat::set_error("input too short for an uncentered frame"); return AMTFEAT_ERR_INVALID; }
+    if (T < 0) { amtfeat::set_error("input too short (an uncentered frame longer than the padded signal, or a clip shorter than the early-downsampling factor of a CQT / VQT)"); return AMTFEAT_ERR_INVALID; }
     switch (c.kind) {
         case AMTFEAT_POWER: *ndim = 1; shape[0] = T; shape[1] = shape[2] = 1; break;
         case AMTFEAT_WAVEFORM: *ndim = 2; shape[0] = c.win_length; shape[1] = T; shape[2] = 1; break;

@@ -204,6 +204,10 @@ int64_t output_frames(const Plan &p, int64_t n) {
             return 1 + (np_ - c.win_length) / c.hop_length;
         }
         default: {
+            // librosa __early_downsample: "Input signal length=%d is too short for %d-octave CQT" when a harmonic is downsampled
+            // early by 2^eds and the clip is shorter than that factor (the reference's process_audio then raises)
+            for (size_t h = 0; h < p.harm.size(); ++h)
+                if (p.harm[h].eds_lib > 0 && n < ((int64_t)1 << p.harm[h].eds_lib)) return -1;
             int64_t best = c.kind == AMTFEAT_HVQT ? expected_frames(p, n) : INT64_MAX;  // hvqt.py:123-128 trims
             for (size_t h = 0; h < p.harm.size(); ++h) best = std::min(best, vqt_lib_frames(p, (int)h, n));
             return best;

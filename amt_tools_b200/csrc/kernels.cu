@@ -2196,7 +2196,7 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
     const amtfeat_config &c = p.cfg;
     std::vector<ClipMeta> metas;
     const WsLayout w = ws_layout(p, batch, n, &metas);
-    if (!w.ok) { set_error("input too short for an uncentered frame (n_fft / win_length larger than the padded signal)"); return AMTFEAT_ERR_INVALID; }
+    if (!w.ok) { set_error("input too short (an uncentered frame longer than the padded signal, or a clip shorter than the early-downsampling factor of a CQT / VQT: librosa raises 'Input signal length=... is too short for ...-octave CQT')"); return AMTFEAT_ERR_INVALID; }
     if (ws_bytes < w.total) { set_error("workspace too small"); return AMTFEAT_ERR_WORKSPACE; }
     int maxT = 0, maxTall = 0;
     int64_t maxn = 0;
