@@ -413,3 +413,38 @@ def test_sliding_dft_matches_fft_per_frame(monkeypatch):
     # the HCQT has sliding items: make sure the comparison above was not vacuous
     monkeypatch.delenv('AMTFEAT_SLIDE', raising=False)
     assert sum(it['slide'] for it in ab.HCQT(22050, 256, n_bins=360, bins_per_octave=60).describe()['items'] if not it['alt']) == 6
+
+
+def test_concurrent_callers_of_one_module_on_their_own_streams():
+    """Two host threads call process_audio of the SAME module (one plan: shared descriptor ring, call slots, side streams) on their
+    own CUDA streams; every result must be bit-identical to the single-threaded one."""
+    import threading
+    m = ab.HCQT(22050, 256, n_bins=120, bins_per_octave=24, harmonics=[0.5, 1, 2])
+    mel = ab.MelSpec(16000)
+    clips = [piano_like(22050 * 2 + 100 * i, 22050, seed=40 + i) for i in range(6)]
+    clips16 = [piano_like(16000 * 2 + 64 * i, 16000, seed=50 + i) for i in range(6)]
+    want = [m.process_audio(c).clone() for c in clips]
+    want_mel = [mel.process_audio(c).clone() for c in clips16]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(idx):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for rep in range(15):
+                    i = (idx + rep) % len(clips)
+                    got = m.process_audio(clips[i])
+                    got_mel = mel.process_audio(clips16[i])
+                    st.synchronize()
+                    if not torch.equal(got, want[i]) or not torch.equal(got_mel, want_mel[i]):
+                        errors.append((idx, rep, i))
+        except Exception as e:     # noqa: BLE001
+            errors.append((idx, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
