@@ -27,18 +27,77 @@ def feats_path(save_loc, dataset_name, data_proc, track):
     return os.path.join(save_loc, dataset_name, data_proc.features_name(), '%s.npz' % track)
 
 
-COMPRESS_LEVEL = 1   # deflate level of the compressed cache files
+COMPRESS_LEVEL = 1          # deflate level of the compressed cache files
+_CHUNK = 8 << 20            # bytes of an array one deflate task takes
+_zpool = None
+
+
+def _deflate_pool():
+    global _zpool
+    if _zpool is None:
+        _zpool = ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 2), thread_name_prefix='amtfeat-deflate')
+    return _zpool
+
+
+def _deflate_chunk(args):
+    import zlib
+    chunk, level, last = args
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    return co.compress(chunk) + co.flush(zlib.Z_FINISH if last else zlib.Z_FULL_FLUSH)
 
 
 def _savez_deflate(f, arrays, level):
-    """`np.savez_compressed` with a chosen deflate level: the same zip-of-.npy container (any `np.load` reads it, as the reference's
-    loader does, datasets/common.py:245), but level 1 instead of zlib's default 6 -- on float32 features the files are ~3 % larger
-    and the writer threads, which bound this step (the GPU waits for them), run 1.7x - 3x faster."""
+    """`np.savez_compressed` rewritten for throughput: the same zip-of-.npy container (any `np.load` reads it, as the reference's
+    loader does, datasets/common.py:245), but
+      * deflate level 1 instead of zlib's default 6 (float32 features: files ~3 % larger, 1.7x - 3x faster), and
+      * every array is deflated in 8 MB pieces on a thread pool (zlib releases the GIL) -- each piece ends with a full flush, so the
+        concatenation is one valid deflate stream -- instead of one thread per file: a 178 MB HCQT track no longer waits for a
+        single core.
+    The zip structures (local headers, central directory) are written by hand because zipfile cannot take pre-deflated data;
+    members of 4 GiB or more fall back to zipfile (zip64)."""
+    import io
+    import struct
     import zipfile
-    with zipfile.ZipFile(f, 'w', zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=level) as zf:
-        for key, val in arrays.items():
-            with zf.open(key + '.npy', 'w', force_zip64=True) as fp:
-                np.lib.format.write_array(fp, np.asanyarray(val), allow_pickle=False)
+    import zlib
+    members = []
+    for key, val in arrays.items():
+        arr = np.asanyarray(val)
+        if arr.ndim and not arr.flags.c_contiguous:       # (np.ascontiguousarray would turn the 0-d fs / hop_length into 1-d arrays)
+            arr = np.ascontiguousarray(arr)
+        hdr = io.BytesIO()
+        np.lib.format.write_array_header_1_0(hdr, np.lib.format.header_data_from_array_1_0(arr))
+        members.append((key + '.npy', hdr.getvalue(), arr))
+    if any(len(h) + a.nbytes >= (1 << 32) - 1 for _, h, a in members):
+        with zipfile.ZipFile(f, 'w', zipfile.ZIP_DEFLATED, allowZip64=True, compresslevel=level) as zf:
+            for name, h, a in members:
+                with zf.open(name, 'w', force_zip64=True) as fp:
+                    fp.write(h)
+                    fp.write(a.data)
+        return
+    central = []
+    offset = 0
+    for name, h, a in members:
+        raw = memoryview(np.atleast_1d(a).reshape(-1).view(np.uint8)) if a.nbytes else memoryview(b'')
+        pieces = [bytes(h) + bytes(raw[:max(0, _CHUNK - len(h))])]
+        pos = max(0, _CHUNK - len(h))
+        while pos < len(raw):
+            pieces.append(raw[pos:pos + _CHUNK])
+            pos += _CHUNK
+        tasks = [(pc, level, i == len(pieces) - 1) for i, pc in enumerate(pieces)]
+        comp = list(_deflate_pool().map(_deflate_chunk, tasks)) if len(tasks) > 1 else [_deflate_chunk(tasks[0])]
+        crc = 0
+        for pc in pieces:
+            crc = zlib.crc32(pc, crc)
+        csize, usize = sum(len(c) for c in comp), len(h) + a.nbytes
+        nm = name.encode()
+        f.write(struct.pack('<IHHHHHIIIHH', 0x04034b50, 20, 0, 8, 0, 0x21, crc, csize, usize, len(nm), 0) + nm)
+        for c in comp:
+            f.write(c)
+        central.append(struct.pack('<IHHHHHHIIIHHHHHII', 0x02014b50, 20, 20, 0, 8, 0, 0x21, crc, csize, usize, len(nm), 0, 0, 0, 0, 0, offset) + nm)
+        offset += 30 + len(nm) + csize
+    cd = b''.join(central)
+    f.write(cd)
+    f.write(struct.pack('<IHHHHIIH', 0x06054b50, 0, 0, len(central), len(central), len(cd), offset, 0))
 
 
 def _write(path, fs, hop_length, feats, compressed):
