@@ -160,10 +160,11 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
         shapes, sizes, out_off, _, _, ws_bytes, total_out = data_proc._batch_layout(lens)
         plans.append((batch, lens, in_off, max(total_in, 4), shapes, sizes, out_off, max(total_out, 4), ws_bytes))
     max_in, max_out = max(p[3] for p in plans), max(p[7] for p in plans)
-    ring = max(2, int(ring))
+    ring = max(1, min(max(2, int(ring)), len(plans)))        # no more staging slots (pinned and device memory) than batches
     pipe = Pipeline(data_proc.device.index, ring, max_in, max_out, max(p[8] for p in plans))
-    h_in = [torch.empty(max_in, dtype=torch.float32).pin_memory() for _ in range(ring)]
-    h_out = [torch.empty(max_out, dtype=torch.float32).pin_memory() for _ in range(ring)]
+    # pinned staging buffers, allocated when a slot is first used: page-locking gigabytes takes about as long as writing them out,
+    # so the later slots are locked while the GPU and the writers are already busy with the first batch
+    h_in, h_out = [None] * ring, [None] * ring
     busy = [[] for _ in range(ring)]          # writer futures still reading a host output slot
     out, pending = {}, []
     t_gpu = t_writers = 0.0
@@ -185,7 +186,7 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
         with ThreadPoolExecutor(max_workers=max(1, writers)) as pool:
             for b, plan in enumerate(plans):
                 slot = b % ring
-                while len(pending) >= ring - 1:                                  # keep ring - 1 batches in flight
+                while len(pending) >= max(1, ring - 1):                          # keep ring - 1 batches in flight
                     flush(pending.pop(0), pool)
                 t = time.perf_counter()
                 for fut in busy[slot]:                                           # the writers of batch b - ring are done with this slot
@@ -193,6 +194,9 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
                 t_writers += time.perf_counter() - t
                 busy[slot] = []
                 batch, lens, in_off, total_in, _, _, out_off, total_out, _ = plan
+                if h_in[slot] is None:
+                    h_in[slot] = torch.empty(max_in, dtype=torch.float32, pin_memory=True)
+                    h_out[slot] = torch.empty(max_out, dtype=torch.float32, pin_memory=True)
                 for i, o, n in zip(batch, in_off, lens):
                     a = tracks[names[i]]
                     a = a.detach().cpu() if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
