@@ -161,10 +161,19 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
         plans.append((batch, lens, in_off, max(total_in, 4), shapes, sizes, out_off, max(total_out, 4), ws_bytes))
     max_in, max_out = max(p[3] for p in plans), max(p[7] for p in plans)
     ring = max(1, min(max(2, int(ring)), len(plans)))        # no more staging slots (pinned and device memory) than batches
+    t_setup = time.perf_counter()
     pipe = Pipeline(data_proc.device.index, ring, max_in, max_out, max(p[8] for p in plans))
+    t_setup = time.perf_counter() - t_setup
+    t_alloc = t_fill = 0.0
     # pinned staging buffers, allocated when a slot is first used: page-locking gigabytes takes about as long as writing them out,
     # so the later slots are locked while the GPU and the writers are already busy with the first batch
     h_in, h_out = [None] * ring, [None] * ring
+
+    def alloc_slot(k):
+        return (torch.empty(max_in, dtype=torch.float32, pin_memory=True), torch.empty(max_out, dtype=torch.float32, pin_memory=True))
+
+    alloc_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix='amtfeat-pin')
+    alloc_futs = [alloc_pool.submit(alloc_slot, k) for k in range(ring)]     # slot 0 first; the others lock pages behind the first batch
     busy = [[] for _ in range(ring)]          # writer futures still reading a host output slot
     out, pending = {}, []
     t_gpu = t_writers = 0.0
@@ -195,12 +204,15 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
                 busy[slot] = []
                 batch, lens, in_off, total_in, _, _, out_off, total_out, _ = plan
                 if h_in[slot] is None:
-                    h_in[slot] = torch.empty(max_in, dtype=torch.float32, pin_memory=True)
-                    h_out[slot] = torch.empty(max_out, dtype=torch.float32, pin_memory=True)
+                    t = time.perf_counter()
+                    h_in[slot], h_out[slot] = alloc_futs[slot].result()
+                    t_alloc += time.perf_counter() - t
+                t = time.perf_counter()
                 for i, o, n in zip(batch, in_off, lens):
                     a = tracks[names[i]]
                     a = a.detach().cpu() if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
                     h_in[slot][o:o + n].copy_(a.to(torch.float32))
+                t_fill += time.perf_counter() - t
                 ticket = pipe.submit(data_proc, h_in[slot], in_off, lens, out_off, h_out[slot], total_in, total_out)
                 pending.append((slot, ticket, plan))
             while pending:
@@ -210,10 +222,12 @@ def precompute_features(tracks, data_proc, save_loc, dataset_name, rank=0, world
                 out[k] = out[k].result()
             t_writers += time.perf_counter() - t
     finally:
+        alloc_pool.shutdown(wait=True)
         pipe.wait(-1)
         pipe.close()
     if stats is not None:
-        stats.update(wait_gpu_s=t_gpu, wait_writers_s=t_writers, batches=len(plans), tracks=len(out))
+        stats.update(wait_gpu_s=t_gpu, wait_writers_s=t_writers, pipeline_create_s=t_setup, pinned_alloc_s=t_alloc, fill_s=t_fill,
+                     batches=len(plans), tracks=len(out))
     return out
 
 
