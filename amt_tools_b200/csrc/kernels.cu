@@ -903,7 +903,10 @@ struct TailParams {
 // the final rounding to float32 -- at a quarter of the float64 operations and shared-memory wavefronts of a plain float64 loop.
 // PT = 4 outputs per thread amortises the tap loads; PT = 1 (four times the CTAs) when the pieces of a batch are too few to fill
 // the GPU otherwise (short clips: the launch is latency bound, one thread walking all taps of four outputs).
-template <int PT>
+// EXACT: float64 taps and float64 products (one DFMA per tap).  Used for one-shot factors of 8 and more, where almost all of the
+// input's energy lies in the stop band: the float32 rounding of the taps and of the 4-tap partial sums is relative to that full-band
+// amplitude, and showed as 1.5e-3 dB on a CQT whose top bin sits at 2 % of the Nyquist frequency (tools/fuzz_oracle.py).
+template <int PT, bool EXACT>
 __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParams p) {
     constexpr int kTailPerThread = PT, kTailOut = PT * kThreads;
     extern __shared__ __align__(16) float tsm[];
@@ -944,10 +947,14 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
     const int F = p.factor, D = (p.ntaps - 1) / 2;
     const int nq = ((p.ntaps + F - 1) / F + 3) & ~3;      // taps per phase, padded to a multiple of 4 with zeros
     const int J = kTailOut + nq - 1, JP = J | 1;          // entries per phase (odd pitch)
-    float *hs = tsm, *X = tsm + (size_t)F * nq;           // hs[ph * nq + q] = taps[F q + ph] (16-byte aligned rows: float4 loads)
+    // hs[ph * nq + q] = taps[F q + ph] (16-byte aligned rows: float4 loads); EXACT: the same table in float64
+    float *hs = tsm, *X = tsm + (size_t)F * nq * (EXACT ? 2 : 1);
+    double *hd = reinterpret_cast<double *>(tsm);
     for (int i = threadIdx.x; i < F * nq; i += kThreads) {
         const int ph = i / nq, q = i - ph * nq, k = F * q + ph;
-        hs[i] = k < p.ntaps ? (float)__ldg(p.taps + k) : 0.f;
+        const double h = k < p.ntaps ? __ldg(p.taps + k) : 0.0;
+        if (EXACT) hd[i] = h;
+        else hs[i] = (float)h;
     }
     const long long g0 = (long long)F * (m0 - nq + 1) + D;     // X[ph][j] = x[g0 + F j - ph]
     for (int i = threadIdx.x; i < F * J; i += kThreads) {
@@ -962,6 +969,16 @@ __global__ void __launch_bounds__(kThreads) tail_decimate_kernel(const TailParam
     for (int r = 0; r < kTailPerThread; ++r) acc[r] = 0.0;
     for (int ph = 0; ph < F; ++ph) {
         const float *xp = X + ph * JP + threadIdx.x + nq - 1, *hp = hs + ph * nq;
+        if (EXACT) {
+            const double *hq = hd + ph * nq;
+#pragma unroll 4
+            for (int q = 0; q < nq; ++q) {
+                const double h = hq[q];
+#pragma unroll
+                for (int r = 0; r < kTailPerThread; ++r) acc[r] = fma(h, (double)xp[r * kThreads - q], acc[r]);
+            }
+            continue;
+        }
         for (int q = 0; q < nq; q += 4) {
             const float4 h4 = *reinterpret_cast<const float4 *>(hp + q);
 #pragma unroll
@@ -1764,8 +1781,10 @@ int upload_plan(Plan &p) {
     AMT_CUDA(cudaFuncSetAttribute(decimate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
     AMT_CUDA(cudaFuncSetAttribute(decimate_fft64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    AMT_CUDA(cudaFuncSetAttribute(tail_decimate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    AMT_CUDA((cudaFuncSetAttribute(tail_decimate_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    AMT_CUDA((cudaFuncSetAttribute(tail_decimate_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    AMT_CUDA((cudaFuncSetAttribute(tail_decimate_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
+    AMT_CUDA((cudaFuncSetAttribute(tail_decimate_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     AMT_CUDA(cudaFuncSetAttribute(cqt_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if ((rc = upload_vec(p, p.window, &p.d_window))) return rc;
     if ((rc = upload_vec(p, p.mel_start, &p.d_mel_start))) return rc;
@@ -2435,11 +2454,17 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
                 const int tail_out = wide ? out4 : kThreads;
                 dim3 grid((count + tail_out - 1) / tail_out, batch, 2);
                 const int nq = ((tp.ntaps + tp.factor - 1) / tp.factor + 3) & ~3;
-                const size_t tsmem = ((size_t)tp.factor * ((tail_out + nq - 1) | 1) + (size_t)tp.factor * nq) * sizeof(float);
+                const bool exact = tp.factor >= 8;        // float64 taps and products where the stop band holds nearly all the energy
+                const size_t tsmem = ((size_t)tp.factor * ((tail_out + nq - 1) | 1) + (size_t)tp.factor * nq * (exact ? 2 : 1)) * sizeof(float);
                 if (tsmem > 200 * 1024) { set_error("one-shot early-downsampling filter too long for the tail kernel"); return AMTFEAT_ERR_INVALID; }
                 ProfScope ps(p, "tail_decimate_kernel", tst);
-                if (wide) tail_decimate_kernel<4><<<grid, kThreads, tsmem, tst>>>(tp);
-                else tail_decimate_kernel<1><<<grid, kThreads, tsmem, tst>>>(tp);
+                if (exact) {
+                    if (wide) tail_decimate_kernel<4, true><<<grid, kThreads, tsmem, tst>>>(tp);
+                    else tail_decimate_kernel<1, true><<<grid, kThreads, tsmem, tst>>>(tp);
+                } else {
+                    if (wide) tail_decimate_kernel<4, false><<<grid, kThreads, tsmem, tst>>>(tp);
+                    else tail_decimate_kernel<1, false><<<grid, kThreads, tsmem, tst>>>(tp);
+                }
                 AMT_CUDA(cudaGetLastError());
             }
         }
