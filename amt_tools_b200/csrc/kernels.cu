@@ -53,6 +53,23 @@
 #ifndef AMT_STFT_MINB
 #define AMT_STFT_MINB 2
 #endif
+#ifndef AMT_FFT_MAXREG
+#define AMT_FFT_MAXREG 0       // > 0: register cap of the FFT kernels (instead of the 128 that two CTAs of 256 threads per SM allow): 112 leaves
+#endif                         // room for one CTA of an HBM-bound kernel (dB epilogue, 32 registers) beside two FFT CTAs on an SM
+#if AMT_FFT_MAXREG > 0
+#define AMT_FFT_BOUNDS(minb) __maxnreg__(AMT_FFT_MAXREG)
+#else
+#define AMT_FFT_BOUNDS(minb) __launch_bounds__(kThreads, minb)
+#endif
+#ifndef AMT_EPI_MINB
+#define AMT_EPI_MINB 8         // resident CTAs per SM the dB epilogue is compiled for (8: 32 registers, 64 warps per SM)
+#endif
+#ifndef AMT_EPI_UNROLL
+#define AMT_EPI_UNROLL 2       // independent 16-byte loads in flight per thread of the dB epilogue
+#endif
+#ifndef AMT_EPI_CS
+#define AMT_EPI_CS 0           // 1: streaming (evict-first) loads and stores in the dB epilogue
+#endif
 #ifndef AMT_TAIL_STREAM
 #define AMT_TAIL_STREAM 1      // exact-ladder pieces on their own side stream (0: behind the sliding-DFT launches on the ladder's stream)
 #endif
@@ -230,7 +247,7 @@ __device__ __forceinline__ float store_tile(int rows, float *__restrict__ out, i
 }
 
 template <int NC, int MODE>
-__global__ void __launch_bounds__(kThreads, AMT_STFT_MINB) stft_kernel(const StftParams p) {
+__global__ void AMT_FFT_BOUNDS(AMT_STFT_MINB) stft_kernel(const StftParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, PT = TT + 1, NFFT = 2 * NC;
     extern __shared__ __align__(16) float smem[];
@@ -443,7 +460,7 @@ __device__ __forceinline__ float db_finish(float v, float ref_db, int scale01) {
 
 // `dst` == `src`: in place (device-resident consumers).  `dst` = mapped pinned host memory (amtfeat_pipeline_*, same element offsets):
 // the features are read from HBM once and leave for the host in the same pass -- no second pass over HBM and no separate copy.
-__global__ void __launch_bounds__(kThreads) db_epilogue_kernel(const float *src, float *dst, const ClipMeta *__restrict__ meta,
+__global__ void __launch_bounds__(kThreads, AMT_EPI_MINB) db_epilogue_kernel(const float *src, float *dst, const ClipMeta *__restrict__ meta,
                                                                 const float *__restrict__ maxbuf, int C, int F, int scale01) {
     const int seg = blockIdx.y, b = seg / C, c = seg % C;
     const ClipMeta *cm = meta + b;
@@ -457,14 +474,29 @@ __global__ void __launch_bounds__(kThreads) db_epilogue_kernel(const float *src,
     const long long tail0 = head + (nvec << 2);
     const float4 *i4 = reinterpret_cast<const float4 *>(in + head);
     float4 *o4 = reinterpret_cast<float4 *>(o + head);
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kThreads) {
-        float4 v = i4[i];
+    auto finish4 = [&](float4 v) {
         v.x = db_finish(v.x, ref_db, scale01);
         v.y = db_finish(v.y, ref_db, scale01);
         v.z = db_finish(v.z, ref_db, scale01);
         v.w = db_finish(v.w, ref_db, scale01);
-        o4[i] = v;
+        return v;
+    };
+    // AMT_EPI_UNROLL independent 16-byte loads in flight per thread at 64 resident warps per SM (measured, in place over 1.48 GB:
+    // one load, 48 warps 0.585 ms; two loads, 64 warps 0.422 ms = 7.0 TB/s; four loads at 32 / 48 warps 0.486 / 0.436 ms)
+    constexpr int U = AMT_EPI_UNROLL;
+    const long long stride = (long long)gridDim.x * kThreads;
+    long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = AMT_EPI_CS ? __ldcs(i4 + i + u * stride) : i4[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (AMT_EPI_CS) __stcs(o4 + i + u * stride, finish4(v[u]));
+            else o4[i + u * stride] = finish4(v[u]);
+        }
     }
+    for (; i < nvec; i += stride) o4[i] = finish4(i4[i]);
     if (blockIdx.x == 0) {
         if (threadIdx.x < head) o[threadIdx.x] = db_finish(in[threadIdx.x], ref_db, scale01);
         if (tail0 + threadIdx.x < count) o[tail0 + threadIdx.x] = db_finish(in[tail0 + threadIdx.x], ref_db, scale01);
@@ -1193,7 +1225,7 @@ __device__ __forceinline__ void cqt_fft_phase(const CqtParams &p, const CqtItem 
 //          each D value feeds 4 complex MACs.  Results go through a staging tile (also inside the retired scratch) so
 //          that the global stores are T-contiguous (16-byte vectors when the clip's rows are 16-byte aligned).
 template <int NC, bool HALF>
-__global__ void __launch_bounds__(kThreads, AMT_CQT_MINB) cqt_kernel(const CqtParams p) {
+__global__ void AMT_FFT_BOUNDS(AMT_CQT_MINB) cqt_kernel(const CqtParams p) {
     using L = FftLayout<NC>;
     constexpr int G = L::G, S = L::S, TT = kWarpsPerCta * G, WP2 = L::WARP_PITCH / 2, NFFT = 2 * NC;
     constexpr int FL = TT < 32 ? TT : 32;       // lanes along frames
@@ -1537,7 +1569,7 @@ __device__ __forceinline__ void slide_run(const SlideParams &p, const CqtItem &i
     }
 }
 
-__global__ void __launch_bounds__(kThreads, AMT_SLIDE_CTAS) cqt_slide_kernel(const SlideParams p) {
+__global__ void AMT_FFT_BOUNDS(AMT_SLIDE_CTAS) cqt_slide_kernel(const SlideParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ int s_max[AMTFEAT_MAX_HARMONICS];
     const int tid = threadIdx.x, NT = blockDim.x;
