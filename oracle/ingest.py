@@ -8,9 +8,11 @@ The arithmetic of `librosa.load(sr=fs, mono=True, res_type='kaiser_best')` lives
 image: librosa (unpinned, `librosa>=0.9.1`, requirements.txt:3) -> resampy (0.4.x) for the 'kaiser_*' filters.  resampy's
 published algorithm is restated here: `filters.sinc_window` (Kaiser-windowed sinc, 2**precision table entries per zero
 crossing) and the interpolation loop of `interpn._resample_loop` (left / right wing, linear interpolation between table
-entries, table stride int(scale * num_table)).  PARITY UNPINNED for the resampler: no resampy run, golden vector or test of
-the reference is available here; the known-answer tests in tests/test_ingest.py (DC gain, in-band sinusoid, output length)
-pin the scale chain only.  rms_norm / to_mono follow the reference's own lines.
+entries, table stride int(scale * num_table)).  PARITY UNPINNED against resampy itself: no resampy run, golden vector or test of
+the reference is available here.  What pins the restatement (tests/test_ingest.py): known answers (DC gain, in-band sinusoid,
+output length) and torchaudio's Kaiser-windowed sinc resampler with its documented 'kaiser_best' equivalents, an independent
+implementation that agrees to 1e-6 of the peak on in-band content wherever resampy's table stride is exact (2 : 1, upsampling);
+the transition band and the stride truncation of the other ratios stay recall-only.  rms_norm / to_mono follow the reference's own lines.
 """
 
 import numpy as np
