@@ -913,7 +913,9 @@ std::string describe(const Plan &p) {
             const CqtItem &it = p.items[i];
             o << (i ? ", " : "") << "{\"level\": " << it.level << ", \"n_fft\": " << it.nfft << ", \"hop\": " << it.hop
               << ", \"rows\": " << it.nrows << ", \"blocks\": " << it.nblk << ", \"unique_rows\": " << it.nuniq << ", \"kmin\": " << it.kmin << ", \"kmax\": " << p.item_kmax_true[i] << ", \"kmax_padded\": " << it.kmax
-              << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << ", \"alt\": " << it.alt << "}";
+              << ", \"slide\": " << ((!p.slide_off && is_slide_item(it)) ? 1 : 0) << ", \"alt\": " << it.alt << ", \"block_steps\": [";
+            for (int b = 0; b < it.nblk; ++b) o << (b ? ", " : "") << p.blocks[it.blk0 + b].steps;
+            o << "]}";
         }
         o << "]";
         if (const char *e = std::getenv("AMTFEAT_DESCRIBE_ROWS")) {
