@@ -15,5 +15,7 @@ from .features import (FeatureCombo, FeatureModule, CQT, HCQT, HVQT, MelSpec, Si
 from .stream import AudioStream, FeatureStream
 from . import ingest
 from .ingest import load_normalize_audio, pcm16_to_float, resample, rms_norm, to_mono
+from . import longtrack
+from .longtrack import process_long_audio
 
 __version__ = '0.1.0'

@@ -59,6 +59,9 @@ def _load():
         'amtfeat_workspace_bytes': (C.c_size_t, [P, C.c_int, i64p]),
         'amtfeat_launch_count': (C.c_int, [P, C.c_int, i64p]),
         'amtfeat_process': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, P, C.c_size_t, P]),
+        'amtfeat_process_raw': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, P, C.c_size_t, P]),
+        'amtfeat_range_reference': (C.c_int, [P, P, C.c_int64, C.c_int64, C.c_int64, P, P]),
+        'amtfeat_range_finish': (C.c_int, [P, P, C.c_int64, C.c_int64, C.c_int64, P, P, C.c_int64, C.c_int64, P]),
         'amtfeat_process_host': (C.c_int, [P, P, i64p, i64p, i64p, C.c_int, P, C.c_int64, C.c_int64, P, P, P,
                                            C.c_size_t, P]),
         'amtfeat_pipeline_create': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_size_t, C.POINTER(P)]),

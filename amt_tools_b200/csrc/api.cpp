@@ -161,6 +161,31 @@ int amtfeat_process(const amtfeat_plan *plan, const float *d_audio, const int64_
     }
 }
 
+int amtfeat_process_raw(const amtfeat_plan *plan, const float *d_audio, const int64_t *in_offsets, const int64_t *num_samples,
+                        const int64_t *out_offsets, int batch, float *d_out, void *d_workspace, size_t workspace_bytes,
+                        void *stream) {
+    if (!plan || !in_offsets || !num_samples || !out_offsets) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    try {
+        return amtfeat::process(plan->p, d_audio, in_offsets, num_samples, out_offsets, batch, d_out, d_workspace,
+                                workspace_bytes, stream, /*defer_epilogue=*/true);
+    } catch (const std::exception &e) {
+        amtfeat::set_error(std::string("exception: ") + e.what());
+        return AMTFEAT_ERR_INVALID;
+    }
+}
+
+int amtfeat_range_reference(const amtfeat_plan *plan, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end,
+                            float *d_ref, void *stream) {
+    if (!plan || !d_block || !d_ref) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    return amtfeat::range_reference(plan->p, d_block, frames, t_begin, t_end, d_ref, stream);
+}
+
+int amtfeat_range_finish(const amtfeat_plan *plan, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end,
+                         const float *d_ref, float *d_dst, int64_t dst_frames, int64_t t_dst, void *stream) {
+    if (!plan || !d_block || !d_dst || !d_ref) { amtfeat::set_error("null argument"); return AMTFEAT_ERR_INVALID; }
+    return amtfeat::range_finish(plan->p, d_block, frames, t_begin, t_end, d_ref, d_dst, dst_frames, t_dst, stream);
+}
+
 int amtfeat_process_host(const amtfeat_plan *plan, const float *h_audio, const int64_t *in_offsets,
                          const int64_t *num_samples, const int64_t *out_offsets, int batch, float *h_out,
                          int64_t audio_elems, int64_t out_elems, float *d_audio, float *d_out, void *d_workspace,

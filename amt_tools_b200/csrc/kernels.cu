@@ -504,6 +504,98 @@ __global__ void __launch_bounds__(kThreads, AMT_EPI_MINB) db_epilogue_kernel(con
 }
 
 // ------------------------------------------------------------------------------------------------
+// Long tracks cut into chunks: `ref=np.max` (common.py:199, 224-225) runs over the WHOLE track, so a track whose
+// chunks are computed apart (several GPUs, or one after the other) needs the reference level of every chunk's own frames
+// before any element can be finished.  range_max_kernel reduces the raw (un-referenced) log values of the frames a chunk
+// keeps (its halo frames belong to the neighbours); after the maxima of all chunks are combined (a max over C floats: the one
+// exchange step of the path), range_finish_kernel applies max(v - ref, -80) / 80 + 1 to the kept frames while moving them to
+// their place in the track's (C, F, T) block.  db10 is monotonic, so the maximum of the raw log values IS the log of the
+// maximum: the reference is bit-identical with the one db_epilogue_kernel forms from the raw maximum.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {
+    int *ai = reinterpret_cast<int *>(addr);
+    int old = *ai;
+    while (__int_as_float(old) < v) {
+        const int assumed = old;
+        old = atomicCAS(ai, assumed, __float_as_int(v));
+        if (old == assumed) break;
+    }
+}
+
+// grid (frame tiles, channels): a thread walks the rows of its frames (coalesced along T, four rows in flight)
+__global__ void __launch_bounds__(kThreads) range_max_kernel(const float *__restrict__ blk, int F, long long T, long long t0, long long t1,
+                                                              float *ref) {
+    const float *src = blk + (long long)blockIdx.y * F * T;
+    float m = -INFINITY;
+    for (long long t = t0 + (long long)blockIdx.x * kThreads + threadIdx.x; t < t1; t += (long long)gridDim.x * kThreads) {
+        const float *q = src + t;
+        int f = 0;
+        for (; f + 4 <= F; f += 4) {
+            const float a = q[(long long)f * T], b = q[(long long)(f + 1) * T], c = q[(long long)(f + 2) * T], d = q[(long long)(f + 3) * T];
+            m = fmaxf(m, fmaxf(fmaxf(a, b), fmaxf(c, d)));
+        }
+        for (; f < F; ++f) m = fmaxf(m, q[(long long)f * T]);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > -INFINITY) atomic_max_float(ref + blockIdx.y, m);
+}
+
+// grid (frame tiles, rows, channels); mode 0: copy (linear features), 1: dB rescaled to [0, 1], 2: dB (SignalPower).  A thread
+// moves four frames a tile apart per step (four independent loads in flight; source and destination rows start at arbitrary
+// frames, so the accesses stay 4 bytes wide and coalesced).
+__global__ void __launch_bounds__(kThreads) range_finish_kernel(const float *__restrict__ blk, int F, long long T, long long t0, long long t1,
+                                                                 const float *__restrict__ ref, float *__restrict__ dst, long long T_dst,
+                                                                 long long t_dst, int mode) {
+    const int c = blockIdx.z;
+    const float ref_db = mode ? ref[c] : 0.f;
+    const long long step = (long long)gridDim.x * kThreads * 4;
+    for (int f = blockIdx.y; f < F; f += gridDim.y) {
+        const float *src = blk + ((long long)c * F + f) * T;
+        float *o = dst + ((long long)c * F + f) * T_dst + t_dst - t0;
+        for (long long t = t0 + (long long)blockIdx.x * kThreads * 4 + threadIdx.x; t < t1; t += step) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = t + u * kThreads < t1 ? src[t + u * kThreads] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u * kThreads < t1) o[t + u * kThreads] = mode ? db_finish(v[u], ref_db, mode == 1) : v[u];
+        }
+    }
+}
+
+static int range_mode(const Plan &p) { return !has_db_epilogue(p) ? 0 : p.cfg.kind == AMTFEAT_POWER ? 2 : 1; }
+
+int range_reference(const Plan &p, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end, float *d_ref, void *stream) {
+    if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
+    if (t_begin < 0 || t_end > frames || t_begin > t_end) { set_error("frame range outside the block"); return AMTFEAT_ERR_INVALID; }
+    if (t_begin == t_end || !has_db_epilogue(p)) return AMTFEAT_OK;
+    DeviceGuard guard(p.device);
+    const int64_t w = t_end - t_begin;
+    dim3 grid((unsigned)std::min<int64_t>((w + kThreads - 1) / kThreads, 148 * 8), p.C);
+    range_max_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_block, p.F, frames, t_begin, t_end, d_ref);
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
+int range_finish(const Plan &p, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end, const float *d_ref, float *d_dst,
+                 int64_t dst_frames, int64_t t_dst, void *stream) {
+    if (p.device < 0) { set_error("host-only plan: no CUDA device (there is no CPU compute path)"); return AMTFEAT_ERR_NO_DEVICE; }
+    if (t_begin < 0 || t_end > frames || t_begin > t_end || t_dst < 0 || t_dst + (t_end - t_begin) > dst_frames) {
+        set_error("frame range outside the source or the destination block");
+        return AMTFEAT_ERR_INVALID;
+    }
+    if (t_begin == t_end) return AMTFEAT_OK;
+    DeviceGuard guard(p.device);
+    const int64_t w = t_end - t_begin;
+    dim3 grid((unsigned)std::min<int64_t>((w + 4 * kThreads - 1) / (4 * kThreads), 148 * 8), (unsigned)std::min(p.F, 1024), p.C);
+    range_finish_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_block, p.F, frames, t_begin, t_end, d_ref, d_dst,
+                                                                                        dst_frames, t_dst, range_mode(p));
+    AMT_CUDA(cudaGetLastError());
+    return AMTFEAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4 : 2:1 decimator.  y[m] = sum_k h[k] x[2m + D - k], D = (ntaps - 1) / 2 (even), zero extension,
 // h already scaled by sqrt(2) (librosa.resample(scale=True)).  Split into the two polyphase branches
 // so every shared-memory access is unit stride.

@@ -236,5 +236,9 @@ int process(const Plan &p, const float *d_audio, const int64_t *in_off, const in
 bool has_db_epilogue(const Plan &p);
 size_t stft_smem_bytes(const Plan &p);   // dynamic shared memory of stft_kernel for this (STFT / MEL) configuration
 int epilogue_out(const Plan &p, const float *d_out, void *d_ws, int batch, int maxT, float *dst, bool few_ctas, void *stream);
+// chunks of a long track: reference level of a frame range of a raw block, and the epilogue with an external reference
+int range_reference(const Plan &p, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end, float *d_ref, void *stream);
+int range_finish(const Plan &p, const float *d_block, int64_t frames, int64_t t_begin, int64_t t_end, const float *d_ref, float *d_dst,
+                 int64_t dst_frames, int64_t t_dst, void *stream);
 
 }  // namespace amtfeat

@@ -215,8 +215,9 @@ class FeatureModule(object):
             cache[key] = lay
         return lay
 
-    def _launch(self, buf, offsets, lengths):
-        """Enqueue the native path on the current stream; returns the flat output buffer and the batch layout."""
+    def _launch(self, buf, offsets, lengths, raw=False):
+        """Enqueue the native path on the current stream; returns the flat output buffer and the batch layout.
+        `raw`: without the dB epilogue (amtfeat_process_raw; chunks of a long track, longtrack.py)."""
         plan = self._dev_plan
         lay = self._batch_layout(lengths)
         shapes, sizes, out_offsets, out_arr, n_arr, ws_bytes, total = lay
@@ -226,8 +227,9 @@ class FeatureModule(object):
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
                 stream = torch.cuda.current_stream(self.device).cuda_stream
                 in_arr = _lib.i64_array(offsets) if isinstance(offsets, (list, tuple)) else offsets
-                _lib.check(_lib.lib.amtfeat_process(plan.handle, buf.data_ptr(), in_arr, n_arr, out_arr,
-                                                    len(lengths), out.data_ptr(), ws.data_ptr(), ws_bytes, stream))
+                fn = _lib.lib.amtfeat_process_raw if raw else _lib.lib.amtfeat_process
+                _lib.check(fn(plan.handle, buf.data_ptr(), in_arr, n_arr, out_arr,
+                              len(lengths), out.data_ptr(), ws.data_ptr(), ws_bytes, stream))
                 # the caching allocator keeps `ws` / `buf` alive for this stream's pending work
         return out, lay
 

@@ -136,6 +136,28 @@ AMTFEAT_API int amtfeat_process(const amtfeat_plan *plan, const float *d_audio, 
                     void *d_workspace, size_t workspace_bytes, void *stream);
 
 /*
+ * One long track computed as chunks (several GPUs, or one chunk after the other).  The reference normalises a track by ITS
+ * maximum (`ref=np.max`, features/common.py:199, 224-225; mel.py:94; power.py:55), so chunks computed apart need one
+ * exchange step: the maximum over all chunks of C floats.
+ *   amtfeat_process_raw       amtfeat_process without the dB epilogue: a dB plan leaves 10 log10(max(amin, power)) (no
+ *                             reference, no floor, no rescaling) in d_out; a linear plan leaves its final values
+ *   amtfeat_range_reference   d_ref[c] = max(d_ref[c], max over rows and frames [t_begin, t_end) of channel c of the
+ *                             (C, F, frames) block at d_block); the caller initialises d_ref (C floats) with -inf.
+ *                             log10 is monotonic: this is the log of the maximum, bit for bit what amtfeat_process uses
+ *   amtfeat_range_finish      frames [t_begin, t_end) of the raw block -> frames [t_dst, ...) of the (C, F, dst_frames) block
+ *                             at d_dst, through max(v - ref[c], -80) / 80 + 1 (SignalPower: no rescaling; linear plans: copy)
+ * Deviation: an HVQT / HCQT harmonic whose own VQT is a frame or two longer than the common frame count (hvqt.py:123-128) has
+ * its maximum taken over the stored frames only on this path.
+ */
+AMTFEAT_API int amtfeat_process_raw(const amtfeat_plan *plan, const float *d_audio, const int64_t *in_offsets,
+                    const int64_t *num_samples, const int64_t *out_offsets, int batch, float *d_out,
+                    void *d_workspace, size_t workspace_bytes, void *stream);
+AMTFEAT_API int amtfeat_range_reference(const amtfeat_plan *plan, const float *d_block, int64_t frames, int64_t t_begin,
+                    int64_t t_end, float *d_ref, void *stream);
+AMTFEAT_API int amtfeat_range_finish(const amtfeat_plan *plan, const float *d_block, int64_t frames, int64_t t_begin,
+                    int64_t t_end, const float *d_ref, float *d_dst, int64_t dst_frames, int64_t t_dst, void *stream);
+
+/*
  * Same, with HOST buffers (pinned for full PCIe speed): copies the audio to d_audio, runs
  * amtfeat_process, copies the features back to h_out -- all stream-ordered on `stream`, no sync.
  * d_audio / d_out are caller-provided device staging buffers large enough for the batch.
