@@ -370,6 +370,53 @@ def device_leg(ab, torch, dist, dev, wl, world, rank, steps, batch=None):
                   'its data in the 126 MB L2' % (len(copies), len(copies) * in_bytes / 1e6, len(copies))}
 
 
+def longtrack_leg(ab, torch, dist, dev, world, rank, minutes=30.0):
+    """ONE long track (the HCQT of c5) over all N GPUs (amt_tools_b200.longtrack: chunks dealt to the ranks, one all_reduce(MAX) of C
+    floats -- the path's only exchange step), next to process_audio of the whole track on one GPU.  Audio resident on every rank."""
+    from amt_tools_b200 import longtrack as lt
+    name, kw, sr = WORKLOADS['c5'][1][0]
+    n = int(sr * 60 * minutes)
+    seg = synth_batch(sr, 60.0, 1, seed0=4242)[0]
+    y = np.tile(seg, n // len(seg) + 1)[:n].copy()
+    y *= (1.0 + 0.1 * np.sin(np.arange(n, dtype=np.float32) * 1e-6)).astype(np.float32)
+    yd = torch.from_numpy(y).to(dev)
+    m = getattr(ab, name)(device=dev, **kw)
+    group = dist.group.WORLD if world > 1 else None
+
+    def timed(fn):
+        best = None
+        for i in range(4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            if i:           # the first call builds plans / warms the allocator
+                best = float(ms.item()) if best is None else min(best, float(ms.item()))
+        return best, out
+
+    ms_whole, whole = timed(lambda: m.process_audio(yd))
+    ms_chunk, own = timed(lambda: lt.process_long_audio(m, yd, group=group, gather=False))
+    worst = 0.0
+    for f0, f1, part in own.values():
+        w = whole[..., f0:f1]
+        worst = max(worst, float((part - w).abs()[w > 0.25].max()) * 80.0)
+    wt = torch.tensor([worst], device=dev)
+    if world > 1:
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+    hours = minutes / 60.0
+    return {'workload': 'one %.0f-minute track, %s of c5, cut into chunks over %d GPU(s)' % (minutes, name, world),
+            'value': hours / (ms_chunk * 1e-3), 'ms': ms_chunk, 'whole_track_one_gpu_value': hours / (ms_whole * 1e-3), 'whole_track_one_gpu_ms': ms_whole,
+            'max_db_diff_vs_whole_track_graded_bins': float(wt.item()), 'halo_frames': lt.halo_frames(m, 4096),
+            'collective': 'all_reduce(MAX) of %d floats' % m.get_num_channels() if world > 1 else 'none (one rank)'}
+
+
 def leg_fractions(r, sm_mhz, hbm_peak):
     """Fractions of the two rooflines for one workload leg: algorithmic bytes over the measured HBM peak, algorithmic flops over
     the FP32 FMA peak at the observed SM clock; the binding one is the larger time."""
@@ -708,6 +755,12 @@ def run_ours(args):
         extra = {}
         for wl in ('c2', 'c3', 'c4'):
             extra[wl] = device_leg(ab, torch, dist, dev, wl, world, rank, max(5, min(args.steps, 20)))
+    longtrack = None
+    if args.workload == 'c5' and not args.no_extra:
+        try:
+            longtrack = longtrack_leg(ab, torch, dist, dev, world, rank)
+        except Exception as e:      # the line must still go out; the error is the same on every rank (no rank is left in a collective)
+            longtrack = {'error': '%s: %s' % (type(e).__name__, e)}
     # ---------------- the configs[4] caller end to end: precompute + npz cache (one GPU only: every rank would hit one disk) ----
     cache = None
     if args.workload == 'c5' and world == 1 and not args.no_cache and not args.no_e2e:
@@ -826,6 +879,9 @@ def run_ours(args):
         for wl, r in extra.items():
             for k in ('value', 'ms_per_step', 'hbm_frac', 'fp32_frac', 'roofline_frac'):
                 flat['%s_%s' % (wl, k)] = r[k]
+    if longtrack and 'value' in longtrack:
+        flat['longtrack_value'] = longtrack['value']
+        flat['longtrack_whole_track_one_gpu_value'] = longtrack['whole_track_one_gpu_value']
     if cache is not None:
         flat['e2e_cache_value'] = cache['savez']['value']
         flat['e2e_cache_compressed_value'] = cache['savez_compressed']['value']
@@ -838,7 +894,7 @@ def run_ours(args):
                        'streams': ('one CUDA stream per module, consecutive steps alternate between two stream sets (joined at the end of the timed region)'
                                    if step_sets else 'one CUDA stream per module, joined every step' if mod_streams else 'single stream')},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches * args.steps, 'roofline': roofline, 'cpu_baseline': cpu,
-        'workloads': extra, 'cache': cache,
+        'workloads': extra, 'longtrack': longtrack, 'cache': cache,
     }
     line.update(flat)
     emit(line)
