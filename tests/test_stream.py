@@ -164,3 +164,33 @@ def test_streamed_frames_match_the_oracle_slice_by_slice(name, kw):
     # sits further than that from the float64 truth, no further from it than the float32 oracle is (x 1.5), as in test_gpu_parity
     assert worst_top <= max(1e-3, 1.5 * worst_f32), (name, worst_top, worst_f32)
     assert worst_all <= 1e-2 and worst_lin <= 1e-5, (name, worst_all, worst_lin)
+
+
+@pytest.mark.parametrize('kind', ['numpy', 'torch'])
+def test_frame_ring_keeps_the_last_frames_in_order(kind):
+    """The buffer is a preallocated ring (one column write per hop, one gather per view); it must read like the reference's list."""
+    from amt_tools_b200.stream import _FrameRing
+
+    def frame(v, width=1):
+        a = np.full((2, 3, width), float(v), dtype=np.float32)
+        return a if kind == 'numpy' else torch.from_numpy(a)
+
+    ring, ref = _FrameRing(), []
+    views = []
+    for v in range(8):                                   # size 3: wraps twice
+        ring.push(frame(v), 3)
+        ref = (ref + [v])[-3:]
+        got = ring.stacked()
+        views.append(got)
+        assert tuple(got.shape) == (2, 3, len(ref)) and [float(x) for x in np.asarray(got)[0, 0]] == ref and len(ring) == len(ref)
+        assert [float(np.asarray(f)[0, 0, 0]) for f in ring] == ref
+    assert [float(x) for x in np.asarray(views[4])[0, 0]] == [2.0, 3.0, 4.0]      # earlier views are copies: later hops do not touch them
+    ring.push(frame(8), 5)                               # the buffer size may change between hops: newest frames are kept
+    assert [float(x) for x in np.asarray(ring.stacked())[0, 0]] == [5.0, 6.0, 7.0, 8.0]
+    ring.push(frame(9), 2)
+    assert [float(x) for x in np.asarray(ring.stacked())[0, 0]] == [8.0, 9.0]
+    ring.push(frame(0, width=0), 2)                      # the zero-width frame of a final, empty slice: list form, as the reference
+    assert len(ring) == 2 and tuple(ring.stacked().shape) == (2, 3, 1) and float(np.asarray(ring.stacked())[0, 0, 0]) == 9.0
+    ring.push(frame(10), 2)
+    assert len(ring) == 2 and [float(x) for x in np.asarray(ring.stacked())[0, 0]] == [10.0]
+    assert _FrameRing() == [] and not (ring == [])
