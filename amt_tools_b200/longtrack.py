@@ -92,13 +92,15 @@ class _CudaOps:
             _lib.check(_lib.lib.amtfeat_range_reference(self.m._dev_plan.handle, block.data_ptr(), int(block.shape[-1]), int(k0), int(k1),
                                                         ref.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
 
-    def finish(self, block, k0, k1, ref):
+    def finish(self, block, k0, k1, ref, dst=None, t_dst=0):
+        """Frames [k0, k1) of the raw block, finished against `ref`: into a new (C, F, k1 - k0) tensor, or into frames
+        [t_dst, ...) of `dst` (the track's (C, F, T) block)."""
         if not 0 <= k0 <= k1 <= int(block.shape[-1]):
             raise ValueError('frame range [%d, %d) outside the block of %d frames' % (k0, k1, int(block.shape[-1])))
-        out = torch.empty((self.C, self.F, k1 - k0), dtype=torch.float32, device=self.device)
+        out = dst if dst is not None else torch.empty((self.C, self.F, k1 - k0), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib.amtfeat_range_finish(self.m._dev_plan.handle, block.data_ptr(), int(block.shape[-1]), int(k0), int(k1),
-                                                     ref.data_ptr(), out.data_ptr(), int(k1 - k0), 0,
+                                                     ref.data_ptr(), out.data_ptr(), int(out.shape[-1]), int(t_dst),
                                                      torch.cuda.current_stream(self.device).cuda_stream))
         return out
 
@@ -109,6 +111,10 @@ def process_long_audio(module, audio, chunk_frames=None, halo=None, group=None, 
     passes the same track and uploads only the samples of its own chunks.  `gather=True` returns the whole (C, F, T) block on
     every rank (one broadcast per chunk); `gather=False` returns {chunk index: (f0, f1, tensor)} of the rank's own chunks.
     """
+    if not hasattr(module, '_launch') or not hasattr(module, 'device'):
+        raise TypeError('process_long_audio takes ONE feature module; call it per module of a FeatureCombo')
+    if getattr(audio, 'ndim', 1) != 1:
+        raise ValueError('expected mono-channel (1-D) audio, got shape %s' % (tuple(audio.shape),))
     ops = ops or _CudaOps(module)
     n = int(audio.shape[-1])
     hop = int(module.hop_length)
@@ -132,22 +138,21 @@ def process_long_audio(module, audio, chunk_frames=None, halo=None, group=None, 
         ops.reference(block, k0, k0 + (f1 - f0), ref)
     if distributed:
         dist.all_reduce(ref, op=dist.ReduceOp.MAX, group=group)      # the one exchange step of the path: C floats
-    done = {}
-    for ci, block in blocks.items():
-        f0, f1, a, b, k0 = plan[ci]
-        done[ci] = (f0, f1, ops.finish(block, k0, k0 + (f1 - f0), ref))
-    blocks.clear()
     if not gather:
+        done = {}
+        for ci, block in blocks.items():
+            f0, f1, a, b, k0 = plan[ci]
+            done[ci] = (f0, f1, ops.finish(block, k0, k0 + (f1 - f0), ref))
         return done
-    parts = []
+    # the whole block on every rank: own chunks are finished straight into their place, the others arrive by broadcast
+    full = torch.empty((ops.C, ops.F, T), dtype=torch.float32, device=ops.device)
     for ci, (f0, f1, a, b, k0) in enumerate(plan):
-        if ci in done:
-            part = done[ci][2]
-        else:
-            part = torch.empty((ops.C, ops.F, f1 - f0), dtype=torch.float32, device=ops.device)
-        if distributed:
-            dist.broadcast(part, src=dist.get_global_rank(group, ci % world), group=group)
-        parts.append(part)
-    full = torch.cat(parts, dim=-1) if parts else torch.empty((ops.C, ops.F, 0), dtype=torch.float32, device=ops.device)
+        if ci in blocks and not distributed:
+            ops.finish(blocks.pop(ci), k0, k0 + (f1 - f0), ref, dst=full, t_dst=f0)
+            continue
+        part = ops.finish(blocks.pop(ci), k0, k0 + (f1 - f0), ref) if ci in blocks else \
+            torch.empty((ops.C, ops.F, f1 - f0), dtype=torch.float32, device=ops.device)
+        dist.broadcast(part, src=dist.get_global_rank(group, ci % world), group=group)
+        full[..., f0:f1] = part
     full = full.reshape(shape)
     return full.cpu().numpy() if getattr(module, 'output', 'torch') == 'numpy' else full

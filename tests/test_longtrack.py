@@ -41,6 +41,14 @@ def test_halo_covers_the_ladder_and_the_exact_pieces():
     assert h % lt.ALIGN == 0 and 384 <= h <= 512
 
 
+def test_rejects_combos_and_batches():
+    mel = ab.MelSpec(sample_rate=16000, hop_length=512)
+    with pytest.raises(TypeError):
+        lt.process_long_audio(ab.FeatureCombo([mel]), np.zeros(16000, dtype=np.float32))
+    with pytest.raises(ValueError):
+        lt.process_long_audio(mel, np.zeros((2, 16000), dtype=np.float32))
+
+
 class _OracleOps:
     """The three steps of a chunk on the CPU (float64 oracle): what _CudaOps does through the C-ABI."""
 
@@ -57,9 +65,23 @@ class _OracleOps:
     def reference(self, block, k0, k1, ref):
         ref.copy_(torch.maximum(ref, block[..., k0:k1].amax(dim=(1, 2)).to(ref.dtype)))
 
-    def finish(self, block, k0, k1, ref):
+    def finish(self, block, k0, k1, ref, dst=None, t_dst=0):
         v = block[..., k0:k1] - ref.to(block.dtype)[:, None, None]
-        return (torch.clamp(v, min=-80.0) / 80 + 1).to(torch.float32)
+        v = (torch.clamp(v, min=-80.0) / 80 + 1).to(torch.float32)
+        if dst is None:
+            return v
+        dst[..., t_dst:t_dst + (k1 - k0)] = v
+        return dst
+
+
+def test_one_rank_chunks_equal_the_whole_track_on_the_oracle():
+    sr, hop = 16000, 512
+    audio = piano_like(sr * 8, sr, seed=6)
+    mod = ab.MelSpec(sample_rate=sr, hop_length=hop, n_fft=2048, n_mels=40)
+    ops = _OracleOps(om.OMelSpec(sample_rate=sr, hop_length=hop, n_fft=2048, n_mels=40, decibels=False), 1, 40)
+    full = lt.process_long_audio(mod, audio, chunk_frames=128, ops=ops).numpy()
+    want = om.OMelSpec(sample_rate=sr, hop_length=hop, n_fft=2048, n_mels=40).process_audio(audio.astype(np.float64))
+    assert full.shape == want.shape and np.abs(full - want).max() * 80 < 1e-4 and full.max() == 1.0
 
 
 def _free_port():
