@@ -662,17 +662,17 @@ def run_ours(args):
         # The other consumer the north_star names: a model on the same GPU (OnsetsFrames / TabCNN pre_proc) takes the
         # features as device tensors.  Public Python API, pinned host audio in, features stay resident, and the step's
         # result read back is one scalar per track (mean feature value).
-        rstreams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-        rhost = [torch.empty(len(mods), B, dtype=torch.float32).pin_memory() for _ in range(2)]
+        NRS = max(2, args.consumer_streams)     # steps in flight: the upload of step i + 1 (+ 2 ...) overlaps the kernels of step i
+        rstreams = [torch.cuda.Stream(dev) for _ in range(NRS)]
+        rhost = [torch.empty(len(mods), B, dtype=torch.float32).pin_memory() for _ in range(NRS)]
 
         def step_resident(i):
-            # alternate two streams: the upload of step i+1 overlaps the kernels of step i
-            with torch.cuda.stream(rstreams[i % 2]):
+            with torch.cuda.stream(rstreams[i % NRS]):
                 res = []
                 for m, ha in zip(mods, host_audio):
                     f = m.process_audio(ha.to(dev, non_blocking=True))
                     res.append(f.reshape(B, -1).mean(dim=1))
-                rhost[i % 2].copy_(torch.stack(res), non_blocking=True)
+                rhost[i % NRS].copy_(torch.stack(res), non_blocking=True)
 
         for i in range(4):
             step_resident(i)
@@ -687,7 +687,7 @@ def run_ours(args):
             torch.cuda.current_stream(dev).wait_stream(st)
         r1.record()
         barrier()
-        last = rhost[(args.steps - 1) % 2]
+        last = rhost[(args.steps - 1) % NRS]
         rms = torch.tensor([r0.elapsed_time(r1)], device=dev)
         if world > 1:
             dist.all_reduce(rms, op=dist.ReduceOp.MAX)
@@ -696,12 +696,12 @@ def run_ours(args):
         host_pcm = [torch.round(a / sc).to(torch.int16).pin_memory() for a, sc in zip(host_audio, pcm_scale)]
 
         def step_resident_pcm(i):
-            with torch.cuda.stream(rstreams[i % 2]):
+            with torch.cuda.stream(rstreams[i % NRS]):
                 res = []
                 for m, hp, sc in zip(mods, host_pcm, pcm_scale):
                     f = m.process_audio(ab.pcm16_to_float(hp.to(dev, non_blocking=True), sc, device=dev))
                     res.append(f.reshape(B, -1).mean(dim=1))
-                rhost[i % 2].copy_(torch.stack(res), non_blocking=True)
+                rhost[i % NRS].copy_(torch.stack(res), non_blocking=True)
 
         for i in range(4):
             step_resident_pcm(i)
@@ -747,7 +747,7 @@ def run_ours(args):
             'h2d_bytes_per_step': int(sum(4 * B * n for n in n_per)), 'd2h_bytes_per_step': int(4 * B * len(mods)),
             'ms_per_step': float(rms.item()) / args.steps,
             'path': 'FeatureModule.process_audio (Python API): pinned host audio -> H2D -> kernels; features stay on the '
-                    'device for the model, one float per track and module read back', 'checksum': float(last.sum()),
+                    'device for the model, one float per track and module read back; %d steps in flight (one stream each)' % NRS, 'checksum': float(last.sum()),
         }
     # ---------------- the other named shapes (BASELINE.json configs[1..3]), device resident, same run ----------------
     extra = None
@@ -932,6 +932,7 @@ def main():
     ap.add_argument('--serial-steps', action='store_true', help='join every step on the current stream (A/B for the step pipelining)')
     ap.add_argument('--no-bind', action='store_true', help='do not pin the rank to the CPU cores next to its GPU (A/B)')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--consumer-streams', type=int, default=4, help='steps in flight of the device-consumer legs (one CUDA stream each)')
     ap.add_argument('--no-extra', action='store_true', help='skip the device-resident legs of the other named workloads (c2, c3, c4)')
     ap.add_argument('--no-cache', action='store_true', help='skip the precompute + npz cache leg')
     ap.add_argument('--cache-tracks', type=int, default=16, help='tracks of the precompute + cache leg (np.savez; a quarter of them compressed)')
