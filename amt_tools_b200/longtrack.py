@@ -9,7 +9,7 @@ cut on frame boundaries, every chunk extended by a halo of frames that are compu
 computed apart -- up to ONE exchange: the per-channel maximum over all chunks (C floats, `all_reduce(MAX)`), the only
 collective this path has.  Each chunk is then finished against the track's reference while it moves to its place.
 
-    feats = process_long_audio(module, audio)                      # one GPU, chunk after chunk
+    feats = process_long_audio(module, audio, chunk_frames=16384)  # one GPU, chunk after chunk (a memory budget)
     feats = process_long_audio(module, audio, group=dist.group.WORLD)   # chunks dealt round-robin to the ranks
 
 Results equal `module.process_audio(audio)` up to float32 rounding (the fast-convolution blocks of the ladder and the
@@ -122,6 +122,10 @@ def process_long_audio(module, audio, chunk_frames=None, halo=None, group=None, 
     T = int(shape[-1]) if len(shape) else 0
     distributed = group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if distributed else (0, 1)
+    if chunk_frames is None and world == 1 and ops.__class__ is _CudaOps:
+        # one rank and no chunk size asked for: the track is one call (chunking on one GPU only serves a memory budget)
+        full = module.process_audio(audio)
+        return full if gather else {0: (0, T, full.reshape(ops.C, ops.F, T) if isinstance(full, torch.Tensor) else full)}
     if chunk_frames is None:
         chunk_frames = max(16 * ALIGN, -(-T // (4 * world)))       # a few chunks per rank: the halo stays a small share
     if halo is None:

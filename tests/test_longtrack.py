@@ -197,3 +197,14 @@ def test_range_entry_points_reject_bad_ranges():
         ops.reference(block, 0, int(block.shape[-1]) + 1, ref)
     with pytest.raises(ValueError):
         ops.finish(block, 5, 3, ref)
+
+
+@pytest.mark.gpu
+def test_one_rank_default_is_the_whole_track_call():
+    dev = torch.device('cuda', 0)
+    m = ab.HCQT(sample_rate=22050, hop_length=256, n_bins=360, bins_per_octave=60, device=dev)
+    yd = torch.from_numpy(piano_like(22050 * 20, 22050, seed=13)).to(dev)
+    whole = m.process_audio(yd)
+    assert torch.equal(lt.process_long_audio(m, yd), whole)                     # no chunk size asked for, one rank: one call
+    own = lt.process_long_audio(m, yd, gather=False)
+    assert list(own) == [0] and own[0][:2] == (0, whole.shape[-1]) and torch.equal(own[0][2], whole.reshape(own[0][2].shape))

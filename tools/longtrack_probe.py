@@ -51,7 +51,8 @@ for name, kw in (('HCQT', dict(sample_rate=sr, hop_length=256, n_bins=360, bins_
         return best, out
 
     t_whole, whole = timed(lambda: m.process_audio(yd))
-    t_own, own = timed(lambda: lt.process_long_audio(m, yd, group=group, gather=False))
+    cf = max(16 * lt.ALIGN, -(-int(m._out_shape(n)[-1]) // (4 * world)))
+    t_own, own = timed(lambda: lt.process_long_audio(m, yd, chunk_frames=cf, group=group, gather=False))
     # the rank's own chunks against the whole-track result
     worst = 0.0
     for ci, (f0, f1, part) in own.items():
@@ -59,7 +60,7 @@ for name, kw in (('HCQT', dict(sample_rate=sr, hop_length=256, n_bins=360, bins_
         sel = w > 0.25
         worst = max(worst, float((part - w).abs()[sel].max()) * 80.0)
     del own
-    t_all, full = timed(lambda: lt.process_long_audio(m, yd, group=group, gather=True), reps=2)
+    t_all, full = timed(lambda: lt.process_long_audio(m, yd, chunk_frames=cf, group=group, gather=True), reps=2)
     same_shape = tuple(full.shape) == tuple(whole.shape)
     del full, whole
     torch.cuda.empty_cache()
