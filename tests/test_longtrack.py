@@ -31,6 +31,28 @@ def test_chunk_plan_geometry(n, T, hop, chunk, halo):
     assert all(p[1] - p[0] >= min(halo, T) for p in plan)                                # no chunk that is all halo
 
 
+def test_chunk_plan_invariants_on_random_geometry():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(T=st.integers(0, 400000), hop=st.sampled_from([64, 256, 512, 1024]), chunk=st.integers(1, 100000),
+           halo=st.integers(1, 16).map(lambda k: k * lt.ALIGN), extra=st.integers(0, 1023))
+    def check(T, hop, chunk, halo, extra):
+        n = max(0, (T - 1) * hop + extra) if T else 0        # a centred module: T = 1 + n // hop
+        plan = lt.chunk_plan(n, T, hop, chunk, halo)
+        covered = 0
+        for f0, f1, a, b, k0 in plan:
+            assert f0 == covered and f1 > f0 and f0 % lt.ALIGN == 0
+            covered = f1
+            assert a % (lt.ALIGN * hop) == 0 and 0 <= a <= b <= n and k0 == f0 - a // hop
+            assert (a == 0 and k0 == f0) or k0 == halo
+            assert b == n or b == (f1 + halo) * hop
+            assert f1 == T or T - f1 >= halo                   # what is left for the next chunk is more than a halo
+        assert covered == T
+
+    check()
+
+
 def test_halo_covers_the_ladder_and_the_exact_pieces():
     mel = ab.MelSpec(sample_rate=16000, hop_length=512, n_fft=2048)
     assert lt.halo_frames(mel, 1024) == lt.ALIGN                                          # n_fft / hop = 4 frames, rounded up
