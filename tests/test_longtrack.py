@@ -106,6 +106,41 @@ def test_one_rank_chunks_equal_the_whole_track_on_the_oracle():
     assert full.shape == want.shape and np.abs(full - want).max() * 80 < 1e-4 and full.max() == 1.0
 
 
+class _OracleAmplitudeOps(_OracleOps):
+    """Same, for the modules the reference converts with amplitude_to_db (amin 1e-5 on the magnitude)."""
+
+    def raw(self, chunks):
+        out = []
+        for chunk in chunks:
+            S = np.asarray(self.o.process_audio(np.asarray(chunk, dtype=np.float64)))
+            out.append(torch.from_numpy(20.0 * np.log10(np.maximum(1e-5, S)).reshape(self.C, self.F, -1)))
+        return out
+
+
+@pytest.mark.parametrize('name,kw,chunk', [
+    ('VQT', dict(sample_rate=22050, hop_length=512), 256),
+    # h = 0.5 is early-downsampled by 4 in ONE resample call (its own, longer filter): the halo must cover that reach, too
+    ('HCQT', dict(sample_rate=22050, hop_length=256, n_bins=72, bins_per_octave=12, harmonics=[0.5, 1, 2]), 512),
+])
+def test_halo_is_sufficient_for_the_ladder_on_the_oracle(name, kw, chunk):
+    """The halo geometry checked on the ALGORITHM, independent of the kernels: with the float64 oracle computing the chunks, the
+    frames a chunk keeps equal the whole-track frames down to the float32 rounding of the stored result (every decimation
+    filter of the ladder is a finite FIR, so beyond the halo a frame cannot know where the clip was cut)."""
+    sr = kw['sample_rate']
+    audio = piano_like(sr * 20, sr, seed=21)
+    audio[: len(audio) // 2] *= 0.1
+    m = getattr(ab, name)(**kw)
+    ops = _OracleAmplitudeOps(getattr(om, 'O' + name)(decibels=False, **kw), m.get_num_channels(), m.get_feature_size())
+    halo = lt.halo_frames(m, chunk)
+    got = lt.process_long_audio(m, audio, chunk_frames=chunk, ops=ops).numpy()
+    want = np.asarray(getattr(om, 'O' + name)(**kw).process_audio(audio.astype(np.float64)))
+    assert len(lt.chunk_plan(len(audio), got.shape[-1], kw['hop_length'], max(chunk, 2 * halo), halo)) >= 3
+    assert got.shape == want.shape and np.abs(got - want).max() * 80 < 2e-5
+    # and a halo that is too short does show: the check above is not vacuous
+    short = lt.process_long_audio(m, audio, chunk_frames=chunk, halo=0, ops=ops).numpy()
+    assert np.abs(short - want).max() * 80 > 1e-2
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
